@@ -1,0 +1,155 @@
+// device_utils.cuh -- small device helpers shared by the kernels
+#ifndef SNB_DEVICE_UTILS_CUH_
+#define SNB_DEVICE_UTILS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace snb {
+
+#define SNB_FULL_MASK 0xffffffffu
+
+// all-reduce sum over aligned lane groups of size G (xor butterfly: every
+// lane ends with the bit-identical total)
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(SNB_FULL_MASK, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double group_sum_f64(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(SNB_FULL_MASK, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP) -----------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem,
+                                              uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// ---- counter-based noise for dither ----------------------------------------
+// splitmix64 finaliser: two independent 32-bit uniforms per (seed, frame, pair)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+// Box-Muller: two N(0,1) samples from one 64-bit hash
+__device__ __forceinline__ void gauss_pair(uint64_t seed, uint64_t frame,
+                                           uint32_t pair, float *g0, float *g1) {
+  const uint64_t h = mix64(seed + 0x9e3779b97f4a7c15ull * (frame * 4096ull + pair + 1ull));
+  const uint32_t a = static_cast<uint32_t>(h), b = static_cast<uint32_t>(h >> 32);
+  const float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+  const float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);           // [0,1)
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  *g0 = r * c;
+  *g1 = r * s;
+}
+
+// ---- complex helpers ---------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// in-register 16-point DFT (forward, e^{-2 pi i nk/16}), radix 4x4,
+// natural-order output.  ~168 flops.
+__host__ __device__ __forceinline__ void fft16(float (&re)[16], float (&im)[16]) {
+  const float C1 = 0.92387953251128674f;  // cos(pi/8)
+  const float S1 = 0.38268343236508977f;  // sin(pi/8)
+  const float R2 = 0.70710678118654752f;  // sqrt(1/2)
+  float br[16], bi[16];
+  // stage 1: four 4-point DFTs over n1 (stride 4), results b[n2][k1]
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) {
+    const float ar0 = re[n2], ai0 = im[n2];
+    const float ar1 = re[4 + n2], ai1 = im[4 + n2];
+    const float ar2 = re[8 + n2], ai2 = im[8 + n2];
+    const float ar3 = re[12 + n2], ai3 = im[12 + n2];
+    const float t0r = ar0 + ar2, t0i = ai0 + ai2;
+    const float t1r = ar0 - ar2, t1i = ai0 - ai2;
+    const float t2r = ar1 + ar3, t2i = ai1 + ai3;
+    // (a1 - a3) * (-i) = (im, -re)
+    const float t3r = ai1 - ai3, t3i = -(ar1 - ar3);
+    br[n2 * 4 + 0] = t0r + t2r; bi[n2 * 4 + 0] = t0i + t2i;
+    br[n2 * 4 + 1] = t1r + t3r; bi[n2 * 4 + 1] = t1i + t3i;
+    br[n2 * 4 + 2] = t0r - t2r; bi[n2 * 4 + 2] = t0i - t2i;
+    br[n2 * 4 + 3] = t1r - t3r; bi[n2 * 4 + 3] = t1i - t3i;
+  }
+  // twiddles W16^{n2 k1}
+  // n2=1: k1=1 W1, k1=2 W2, k1=3 W3
+  {
+    float r, i;
+    r = br[5]; i = bi[5]; br[5] = r * C1 + i * S1; bi[5] = i * C1 - r * S1;          // W1 = (C1,-S1)
+    r = br[6]; i = bi[6]; br[6] = (r + i) * R2;    bi[6] = (i - r) * R2;             // W2 = (R2,-R2)
+    r = br[7]; i = bi[7]; br[7] = r * S1 + i * C1; bi[7] = i * S1 - r * C1;          // W3 = (S1,-C1)
+    // n2=2: k1=1 W2, k1=2 W4=-i, k1=3 W6 = (-R2,-R2)
+    r = br[9]; i = bi[9]; br[9] = (r + i) * R2;    bi[9] = (i - r) * R2;
+    r = br[10]; i = bi[10]; br[10] = i;            bi[10] = -r;
+    r = br[11]; i = bi[11]; br[11] = (i - r) * R2; bi[11] = -(r + i) * R2;
+    // n2=3: k1=1 W3, k1=2 W6, k1=3 W9 = -W1 = (-C1, S1)
+    r = br[13]; i = bi[13]; br[13] = r * S1 + i * C1; bi[13] = i * S1 - r * C1;
+    r = br[14]; i = bi[14]; br[14] = (i - r) * R2;    bi[14] = -(r + i) * R2;
+    r = br[15]; i = bi[15]; br[15] = -(r * C1 + i * S1); bi[15] = -(i * C1 - r * S1);
+  }
+  // stage 2: four 4-point DFTs over n2 for each k1; out[k1 + 4 k2]
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    const float ar0 = br[k1], ai0 = bi[k1];
+    const float ar1 = br[4 + k1], ai1 = bi[4 + k1];
+    const float ar2 = br[8 + k1], ai2 = bi[8 + k1];
+    const float ar3 = br[12 + k1], ai3 = bi[12 + k1];
+    const float t0r = ar0 + ar2, t0i = ai0 + ai2;
+    const float t1r = ar0 - ar2, t1i = ai0 - ai2;
+    const float t2r = ar1 + ar3, t2i = ai1 + ai3;
+    const float t3r = ai1 - ai3, t3i = -(ar1 - ar3);
+    re[k1 + 0] = t0r + t2r;  im[k1 + 0] = t0i + t2i;
+    re[k1 + 4] = t1r + t3r;  im[k1 + 4] = t1i + t3i;
+    re[k1 + 8] = t0r - t2r;  im[k1 + 8] = t0i - t2i;
+    re[k1 + 12] = t1r - t3r; im[k1 + 12] = t1i - t3i;
+  }
+}
+
+}  // namespace snb
+#endif

@@ -1,0 +1,1120 @@
+// features.cu -- the fused frame-features kernels (spectrogram / filterbank /
+// MFCC / PLP / energy) and their plan / batch objects.
+//
+// Replaces, for a whole ragged batch in ONE launch, what the reference runs
+// per utterance and per frame on one CPU thread:
+//   OfflineFeatureTpl<F>::Compute -> ExtractWindow/ProcessWindow -> SRFFT ->
+//   ComputePowerSpectrum -> MelBanks::Compute -> log -> DCT/lifter | PLP tail
+// (shennong/processor/base.py:427-431, spectrogram.py:137-140,
+//  plp.py:510-626, energy.py:168-183).
+//
+// Fast path (padded FFT size 512, i.e. 16 kHz / 25 ms and every window of
+// 257..512 samples): persistent CTAs, 256 threads = 16 half-warp "groups";
+// each CTA stages the contiguous int16 PCM span of a tile of <= 32 frames into
+// shared memory with one TMA bulk copy (cp.async.bulk + mbarrier), each group
+// owns one frame: dither / DC removal / log-energy / pre-emphasis / window in
+// registers, the 512-point real FFT as a 256-point complex FFT factored
+// 16 x 16 (two in-register radix-16 butterflies, one padded shared-memory
+// transpose), the real-FFT unpack with half-warp shuffles (each conjugate
+// pair computed once), then warp-local mel / log / DCT / PLP tails.
+// Generic path (any other FFT size, incl. non powers of two): one warp per
+// frame, shared-memory radix-2 FFT or direct DFT, same tails.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "device_utils.cuh"
+#include "snb_internal.h"
+
+namespace snb {
+
+__device__ __forceinline__ int64_t first_sample_of_frame_dev(int64_t frame, const FeatParams &p) {
+  if (p.fo.snip_edges) return frame * p.S;
+  return frame * p.S + p.S / 2 - p.W / 2;
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory views
+// ---------------------------------------------------------------------------
+struct MelView {          // decoded mel blob (in shared or global memory)
+  const int32_t *first, *size, *offset;
+  const float *loudness, *weights;
+};
+
+__device__ __forceinline__ MelView mel_view(const int32_t *blob, int B) {
+  MelView v;
+  v.first = blob;
+  v.size = blob + B;
+  v.offset = blob + 2 * B;
+  v.loudness = reinterpret_cast<const float *>(blob + 3 * B);
+  v.weights = reinterpret_cast<const float *>(blob + 4 * B);
+  return v;
+}
+
+struct TailTables {       // tables the tails read (shared memory in both paths)
+  const float *dct, *lifter, *idft;
+  MelView mel;
+};
+
+// ---------------------------------------------------------------------------
+// tails: from the power spectrum P[0..N/2] (shared memory, private to the
+// lane group) to one output row.  G = lanes per frame (16 or 32); all lanes of
+// the warp execute this in lockstep, `valid` only gates the global stores.
+// scratch: >= B + 2 + lpc_order + 1 floats private to the group.
+// ---------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTables &t,
+                                             float *P, float *scratch, float log_energy,
+                                             float *out_row, bool valid, int gl) {
+  const snb_feat_opts &xo = p.xo;
+  const int half = p.N / 2;
+  if (xo.energy_floor > 0.0f && log_energy < p.log_energy_floor)
+    log_energy = p.log_energy_floor;
+
+  if (xo.kind == SNB_FEAT_SPECTROGRAM) {
+    for (int k = gl; k <= half; k += G) {
+      float v = logf(fmaxf(P[k], FLT_EPSILON));
+      if (k == 0) v = log_energy;
+      if (valid) out_row[k] = v;
+    }
+    return;
+  }
+  const int B = p.B;
+  if (xo.kind == SNB_FEAT_FBANK && !xo.use_power) {
+    for (int k = gl; k <= half; k += G) P[k] = sqrtf(P[k]);
+    __syncwarp();
+  }
+  // mel energies: lane-per-bin sparse dot products
+  float *mel = scratch;  // [B+2]; PLP uses mel[1..B] with duplicated ends
+  const int moff = (xo.kind == SNB_FEAT_PLP) ? 1 : 0;
+  for (int b = gl; b < B; b += G) {
+    const int first = t.mel.first[b], size = t.mel.size[b];
+    const float *w = t.mel.weights + t.mel.offset[b];
+    float acc = 0.0f;
+    for (int i = 0; i < size; ++i) acc = fmaf(w[i], P[first + i], acc);
+    if (xo.kind == SNB_FEAT_FBANK) {
+      if (xo.use_log_fbank) acc = logf(fmaxf(acc, FLT_EPSILON));
+      const int off = (xo.use_energy && !xo.htk_compat) ? 1 : 0;
+      if (valid) out_row[off + b] = acc;
+    } else if (xo.kind == SNB_FEAT_MFCC) {
+      mel[b] = logf(fmaxf(acc, FLT_EPSILON));
+    } else {  // PLP: loudness, compression (plp.py:587-588)
+      mel[moff + b] = powf(acc * t.mel.loudness[b], xo.compress_factor);
+    }
+  }
+  if (xo.kind == SNB_FEAT_FBANK) {
+    if (xo.use_energy && gl == 0 && valid)
+      out_row[xo.htk_compat ? B : 0] = log_energy;
+    return;
+  }
+  __syncwarp();
+  const int nc = xo.num_ceps;
+  if (xo.kind == SNB_FEAT_MFCC) {
+    for (int c = gl; c < nc; c += G) {
+      const float *row = t.dct + c * B;
+      float acc = 0.0f;
+      for (int n = 0; n < B; ++n) acc = fmaf(row[n], mel[n], acc);
+      if (xo.cepstral_lifter != 0.0f) acc *= t.lifter[c];
+      if (c == 0 && xo.use_energy) acc = log_energy;
+      int col = c;
+      if (xo.htk_compat) {
+        if (c == 0) {
+          col = nc - 1;
+          if (!xo.use_energy) acc *= 1.41421356237309504880f;
+        } else {
+          col = c - 1;
+        }
+      }
+      if (valid) out_row[col] = acc;
+    }
+    return;
+  }
+  // ---- PLP tail (plp.py:590-626) ----
+  const int L = xo.lpc_order;       // <= G - 1 (checked at plan creation)
+  if (gl == 0) { mel[0] = mel[1]; mel[B + 1] = mel[B]; }
+  __syncwarp();
+  float *ac = scratch + (B + 2);    // [L+1]
+  for (int i = gl; i <= L; i += G) {
+    const float *row = t.idft + i * (B + 2);
+    float acc = 0.0f;
+    for (int j = 0; j < B + 2; ++j) acc = fmaf(row[j], mel[j], acc);
+    ac[i] = acc;
+  }
+  __syncwarp();
+  // Levinson-Durbin, lanes parallel over the coefficient index j
+  const int gbase = (threadIdx.x & 31) & ~(G - 1);  // first lane of my group
+  float E = ac[0];
+  float lpc = 0.0f;                 // lane j holds lpc[j]
+  for (int i = 0; i < L; ++i) {
+    // ki = (ac[i+1] + sum_{j<i} lpc[j] * ac[i-j]) / E
+    float part = (gl < i) ? lpc * ac[i - gl] : 0.0f;
+    part = group_sum<G>(part);
+    float ki = (ac[i + 1] + part) / E;
+    float c = 1.0f - ki * ki;
+    if (c < 1.0e-5f) c = 1.0e-5f;
+    E *= c;
+    // lpc'[j] = lpc[j] - ki * lpc[i-j-1] (j<i); lpc'[i] = -ki
+    const int src = (i - gl - 1) & (G - 1);
+    const float other = __shfl_sync(SNB_FULL_MASK, lpc, gbase + src);
+    if (gl < i) lpc = lpc - ki * other;
+    else if (gl == i) lpc = -ki;
+  }
+  // ComputeLpc returns -log(1/E); plp.py:603 floors with float64 eps
+  float residual = -logf(1.0f / E);
+  residual = fmaxf(residual, 2.220446049250313e-16f);
+  // LPC -> cepstrum (plp.py:164-168), lane i holds cep[i]
+  float cep = 0.0f;
+  for (int i = 0; i < L; ++i) {
+    // sum_{j<i} (i-j) * lpc[j] * cep[i-j-1]
+    const int src = (i - gl - 1) & (G - 1);
+    const float cj = __shfl_sync(SNB_FULL_MASK, cep, gbase + src);
+    float part = (gl < i) ? static_cast<float>(i - gl) * lpc * cj : 0.0f;
+    part = group_sum<G>(part);
+    const float mine = -lpc - part / static_cast<float>(i + 1);
+    if (gl == i) cep = mine;
+  }
+  // out[0] = residual, out[c] = cep[c-1]; lifter, scale, energy, htk reorder
+  // (nc <= L + 1 <= G: one column per lane; the shuffle is warp-uniform)
+  const float prev = __shfl_sync(SNB_FULL_MASK, cep, gbase + ((gl - 1) & (G - 1)));
+  if (gl < nc) {
+    const int c = gl;
+    float v = (c == 0) ? residual : prev;
+    if (xo.cepstral_lifter != 0.0f) v *= t.lifter[c];
+    if (xo.cepstral_scale != 1.0f) v *= xo.cepstral_scale;
+    if (c == 0 && xo.use_energy) v = log_energy;
+    int col = c;
+    if (xo.htk_compat) col = (c == 0) ? nc - 1 : c - 1;
+    if (valid) out_row[col] = v;
+  }
+}
+
+// energy kind (energy.py:171-183): float64 sum of squares of the processed
+// window, compressed; one float64 per frame
+__device__ __forceinline__ double compress_energy(double e, int mode) {
+  if (e < DBL_MIN) e = DBL_MIN;
+  if (mode == 1) return log(e);
+  if (mode == 2) return sqrt(e);
+  return e;
+}
+
+// ---------------------------------------------------------------------------
+// fast path: N = 512
+// ---------------------------------------------------------------------------
+constexpr int kFastThreads = 256;
+constexpr int kFastGroups = 16;         // half-warps per CTA
+constexpr int kXStride = 17;            // float2 row stride of the transpose buffer
+
+struct FastSmemLayout {                 // byte offsets into dynamic smem
+  int window, tw1, tw2, dct, lifter, idft, mel, pcm, grp, bar, total;
+  int grp_floats, span_cap;
+};
+
+struct FastArgs {
+  FeatParams p;
+  FastSmemLayout sm;
+  const TileDesc *tiles;
+  int64_t ntiles;
+  const int64_t *sample_begin;
+  const int64_t *sample_len;
+  const int64_t *frame_offsets;
+  const int32_t *mel_blobs;
+  const int16_t *pcm;
+  int64_t total_samples;
+  void *out;
+  int64_t ld_out;
+  uint64_t seed;
+  int use_tma;
+};
+
+__global__ void __launch_bounds__(kFastThreads, 3)
+fused_features_512_kernel(const FastArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FeatParams &p = a.p;
+  float *s_window = reinterpret_cast<float *>(smem + a.sm.window);
+  float2 *s_tw1 = reinterpret_cast<float2 *>(smem + a.sm.tw1);   // [k1*16+hl] W256^(hl*k1)
+  float2 *s_tw2 = reinterpret_cast<float2 *>(smem + a.sm.tw2);   // [k2*16+hl] W512^(hl+16k2)
+  float *s_dct = reinterpret_cast<float *>(smem + a.sm.dct);
+  float *s_lifter = reinterpret_cast<float *>(smem + a.sm.lifter);
+  float *s_idft = reinterpret_cast<float *>(smem + a.sm.idft);
+  int32_t *s_mel = reinterpret_cast<int32_t *>(smem + a.sm.mel);
+  int16_t *s_pcm = reinterpret_cast<int16_t *>(smem + a.sm.pcm);
+  float *s_grp_all = reinterpret_cast<float *>(smem + a.sm.grp);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.sm.bar);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int hl = lane & 15;                       // lane within the group
+  const int grp = (tid >> 5) * 2 + (lane >> 4);   // 0..15
+  const int gbase = lane & 16;                    // first lane of my group
+  float *s_grp = s_grp_all + grp * a.sm.grp_floats;
+  float2 *s_x = reinterpret_cast<float2 *>(s_grp);
+
+  const int W = p.W, S = p.S, B = p.B;
+  const snb_feat_opts &xo = p.xo;
+  const int kind = xo.kind;
+
+  // ---- one-time table load ----
+  for (int i = tid; i < 512; i += kFastThreads) s_window[i] = (i < W) ? p.t.window[i] : 0.0f;
+  for (int i = tid; i < 256; i += kFastThreads) {
+    const int k1 = i >> 4, l = i & 15;
+    s_tw1[i] = p.t.tw_half[(l * k1) & 255];
+    if (i < 128) s_tw2[i] = p.t.tw_full[l + 16 * k1];   // k2 = k1 < 8
+  }
+  if (kind == SNB_FEAT_MFCC)
+    for (int i = tid; i < xo.num_ceps * B; i += kFastThreads) s_dct[i] = p.t.dct[i];
+  if (kind == SNB_FEAT_MFCC || kind == SNB_FEAT_PLP)
+    for (int i = tid; i < xo.num_ceps; i += kFastThreads) s_lifter[i] = p.t.lifter[i];
+  if (kind == SNB_FEAT_PLP)
+    for (int i = tid; i < (xo.lpc_order + 1) * (B + 2); i += kFastThreads) s_idft[i] = p.t.idft[i];
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_barrier_init();
+  }
+  int cur_mel = -1;
+  uint32_t parity = 0;
+  TailTables tt;
+  tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
+  tt.mel = mel_view(s_mel, B);
+
+  const bool pair_ok_static = (S % 2) == 0;
+  const float dither = p.fo.dither;
+
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const TileDesc td = a.tiles[tile];
+    __syncthreads();   // previous tile fully consumed (s_pcm, s_mel) + tables visible
+    if (B > 0 && td.mel_idx != cur_mel) {
+      const int32_t *src = a.mel_blobs + static_cast<int64_t>(td.mel_idx) * p.mel_blob_stride;
+      for (int i = tid; i < p.mel_blob_stride; i += kFastThreads) s_mel[i] = src[i];
+      cur_mel = td.mel_idx;
+    }
+    // ---- stage the PCM span of this tile ----
+    const int64_t utt_off = a.sample_begin[td.utt];
+    const int64_t utt_len = a.sample_len[td.utt];
+    const int64_t a0 = first_sample_of_frame_dev(td.f0, p);      // may be < 0
+    const int span = (td.nf - 1) * S + W;
+    int mis = 0;                                                 // samples of misalignment
+    const bool inside = (a0 >= 0) && (a0 + span <= utt_len);
+    bool tma = false;
+    if (a.use_tma && inside) {
+      const int64_t g0 = utt_off + a0;
+      mis = static_cast<int>(g0 & 7);
+      const int64_t gstart = g0 - mis;
+      const int64_t nsamp = (static_cast<int64_t>(span) + mis + 7) & ~7ll;
+      tma = (gstart + nsamp <= a.total_samples);
+      if (tma) {
+        if (tid == 0) {
+          fence_proxy_async();
+          const uint32_t bytes = static_cast<uint32_t>(nsamp * 2);
+          mbar_arrive_expect_tx(s_bar, bytes);
+          bulk_copy_g2s(s_pcm, a.pcm + gstart, bytes, s_bar);
+        }
+      } else {
+        mis = 0;
+      }
+    }
+    if (!tma) {
+      // element loads with reflection at the utterance edges (snip_edges=False,
+      // ExtractWindow restated at plp.py:239-254) or unaligned tail tiles
+      const int16_t *src = a.pcm + utt_off;
+      for (int i = tid; i < span; i += kFastThreads) {
+        int64_t k = a0 + i;
+        while (k < 0 || k >= utt_len) k = (k < 0) ? (-k - 1) : (2 * utt_len - 1 - k);
+        s_pcm[i] = src[k];
+      }
+    }
+    if (tma) { mbar_wait(s_bar, parity); parity ^= 1u; }
+    __syncthreads();
+
+    const int64_t row0 = a.frame_offsets[td.utt] + td.f0;
+    for (int base = 0; base < td.nf; base += kFastGroups) {
+      const int fl = base + grp;
+      const bool valid = fl < td.nf;
+      const int fidx = valid ? fl : td.nf - 1;     // idle groups redo the last frame
+      const int16_t *fr = s_pcm + mis + fidx * S;
+      const bool pair_ok = pair_ok_static && ((mis & 1) == 0);
+      float xr[16], xi[16];
+      // ---- load + int16 -> float (+ dither) ----
+      float lsum = 0.0f;
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int i0 = 2 * (16 * n1 + hl);
+        float v0 = 0.0f, v1 = 0.0f;
+        if (i0 < W) {
+          if (pair_ok && i0 + 1 < W) {
+            const int32_t pr = *reinterpret_cast<const int32_t *>(fr + i0);
+            v0 = static_cast<float>(static_cast<int16_t>(pr & 0xffff));
+            v1 = static_cast<float>(pr >> 16);
+          } else {
+            v0 = static_cast<float>(fr[i0]);
+            if (i0 + 1 < W) v1 = static_cast<float>(fr[i0 + 1]);
+          }
+          if (dither != 0.0f) {
+            float g0, g1;
+            gauss_pair(a.seed, static_cast<uint64_t>(row0 + fidx), i0 >> 1, &g0, &g1);
+            v0 = fmaf(dither, g0, v0);
+            if (i0 + 1 < W) v1 = fmaf(dither, g1, v1);
+          }
+        }
+        xr[n1] = v0; xi[n1] = v1;
+        lsum += v0 + v1;
+      }
+      // ---- DC removal (ProcessWindow) ----
+      if (p.fo.remove_dc_offset) {
+        const float mean = __fdiv_rn(group_sum<16>(lsum), static_cast<float>(W));
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+          const int i0 = 2 * (16 * n1 + hl);
+          if (i0 < W) xr[n1] -= mean;
+          if (i0 + 1 < W) xi[n1] -= mean;
+        }
+      }
+      // ---- raw log-energy / float64 energy ----
+      float log_energy = 0.0f;
+      if (p.need_raw_energy) {
+        float e = 0.0f;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
+        e = group_sum<16>(e);
+        log_energy = logf(fmaxf(e, p.eps_energy));
+      }
+      // ---- pre-emphasis (needs the ORIGINAL previous sample) ----
+      if (p.fo.preemph_coeff != 0.0f) {
+        const float c = p.fo.preemph_coeff;
+#pragma unroll
+        for (int n1 = 15; n1 >= 0; --n1) {
+          const float send = (hl == 15) ? xi[(n1 + 15) & 15] : xi[n1];
+          float prev = __shfl_sync(SNB_FULL_MASK, send, gbase | ((hl + 15) & 15));
+          if (n1 == 0 && hl == 0) prev = xr[0];
+          xi[n1] = fmaf(-c, xr[n1], xi[n1]);
+          xr[n1] = fmaf(-c, prev, xr[n1]);
+        }
+      }
+      // ---- window (zero beyond W: also clears pre-emphasis spill) ----
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const float2 w = *reinterpret_cast<const float2 *>(s_window + 2 * (16 * n1 + hl));
+        xr[n1] *= w.x; xi[n1] *= w.y;
+      }
+      if (kind == SNB_FEAT_ENERGY) {
+        double e = 0.0;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1)
+          e += static_cast<double>(xr[n1]) * xr[n1] + static_cast<double>(xi[n1]) * xi[n1];
+        e = group_sum_f64<16>(e);
+        if (valid && hl == 0)
+          reinterpret_cast<double *>(a.out)[(row0 + fl) * a.ld_out] =
+              compress_energy(e, xo.energy_compression);
+        continue;
+      }
+      if (p.need_post_energy) {
+        float e = 0.0f;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
+        e = group_sum<16>(e);
+        log_energy = logf(fmaxf(e, p.eps_energy));
+      }
+
+      // ---- 256-point complex FFT = 16 x 16 ----
+      fft16(xr, xi);                                  // over n1; lane = n2
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) {
+        const float2 w = s_tw1[k1 * 16 + hl];
+        const float r = xr[k1], i = xi[k1];
+        xr[k1] = r * w.x - i * w.y;
+        xi[k1] = r * w.y + i * w.x;
+      }
+      __syncwarp();                                   // previous P readers done
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) s_x[k1 * kXStride + hl] = make_float2(xr[k1], xi[k1]);
+      __syncwarp();
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) {
+        const float2 v = s_x[hl * kXStride + n2];
+        xr[n2] = v.x; xi[n2] = v.y;
+      }
+      fft16(xr, xi);                                  // over n2; Z[hl + 16 k2]
+      __syncwarp();                                   // transpose buffer free -> reuse as P
+      float *P = s_grp;
+      // ---- real-FFT unpack: pairs (k, 256-k), k = hl + 16 k2, k2 < 8 ----
+      const int partner = gbase | ((16 - hl) & 15);
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const float sr = (hl == 0) ? xr[(16 - k2) & 15] : xr[15 - k2];
+        const float si = (hl == 0) ? xi[(16 - k2) & 15] : xi[15 - k2];
+        const float cr = __shfl_sync(SNB_FULL_MASK, sr, partner);   // Z[256-k]
+        const float ci = __shfl_sync(SNB_FULL_MASK, si, partner);
+        const float ar = xr[k2], ai = xi[k2];
+        const int k = hl + 16 * k2;
+        if (k == 0) {
+          const float s0 = ar + ai, d0 = ar - ai;
+          P[0] = s0 * s0;
+          P[256] = d0 * d0;
+        } else {
+          const float2 w = s_tw2[k2 * 16 + hl];
+          const float er = ar + cr, ei = ai - ci;      // 2E
+          const float u = ai + ci, v = cr - ar;        // -i * (Z - conj Zp)
+          const float orr = w.x * u - w.y * v, oi = w.x * v + w.y * u;   // 2 W O
+          const float x1r = er + orr, x1i = ei + oi;
+          const float x2r = er - orr, x2i = ei - oi;
+          P[k] = 0.25f * (x1r * x1r + x1i * x1i);
+          P[256 - k] = 0.25f * (x2r * x2r + x2i * x2i);
+        }
+      }
+      if (hl == 0) P[128] = xr[8] * xr[8] + xi[8] * xi[8];
+      __syncwarp();
+
+      float *out_row = reinterpret_cast<float *>(a.out) + (row0 + fl) * a.ld_out;
+      feature_tail<16>(p, tt, P, s_grp + 272, log_energy, out_row, valid, hl);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// generic path: any FFT size; one warp per frame
+// ---------------------------------------------------------------------------
+constexpr int kGenWarps = 4;
+
+struct GenArgs {
+  FeatParams p;
+  int log2n;                 // -1 when N is not a power of two
+  int warp_floats;           // floats of private smem per warp
+  int tables_floats;         // floats of shared tables (dct|lifter|idft)
+  const int64_t *sample_begin;
+  const int64_t *sample_len;
+  const int64_t *frame_offsets;
+  const int32_t *utt_mel_idx;
+  const int32_t *mel_blobs;
+  const int16_t *pcm;
+  const float *pcm_f32;      // float input (energy kind) when non-null
+  int64_t nutts, total_frames;
+  void *out;
+  int64_t ld_out;
+  uint64_t seed;
+};
+
+__device__ __forceinline__ int64_t find_utt(const int64_t *offsets, int64_t nutts, int64_t row) {
+  int64_t lo = 0, hi = nutts;      // offsets[lo] <= row < offsets[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kGenWarps * 32)
+generic_features_kernel(const GenArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FeatParams &p = a.p;
+  float *s_tables = reinterpret_cast<float *>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const snb_feat_opts &xo = p.xo;
+  const int W = p.W, N = p.N, B = p.B, half = N / 2;
+  float *s_dct = s_tables;
+  float *s_lifter = s_dct + ((xo.kind == SNB_FEAT_MFCC) ? xo.num_ceps * B : 0);
+  float *s_idft = s_lifter + xo.num_ceps;
+  if (xo.kind == SNB_FEAT_MFCC)
+    for (int i = tid; i < xo.num_ceps * B; i += blockDim.x) s_dct[i] = p.t.dct[i];
+  if (xo.kind == SNB_FEAT_MFCC || xo.kind == SNB_FEAT_PLP)
+    for (int i = tid; i < xo.num_ceps; i += blockDim.x) s_lifter[i] = p.t.lifter[i];
+  if (xo.kind == SNB_FEAT_PLP)
+    for (int i = tid; i < (xo.lpc_order + 1) * (B + 2); i += blockDim.x) s_idft[i] = p.t.idft[i];
+  __syncthreads();
+  float *buf_a = s_tables + a.tables_floats + static_cast<int64_t>(warp) * a.warp_floats;  // [N]
+  float *buf_b = buf_a + N;                                                                // [N]
+  float *scratch = buf_b + N;
+
+  TailTables tt;
+  tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
+
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * kGenWarps + warp; row < a.total_frames;
+       row += static_cast<int64_t>(gridDim.x) * kGenWarps) {
+    const int64_t utt = find_utt(a.frame_offsets, a.nutts, row);
+    const int64_t f = row - a.frame_offsets[utt];
+    const int64_t utt_off = a.sample_begin[utt];
+    const int64_t n = a.sample_len[utt];
+    const int64_t start = first_sample_of_frame_dev(f, p);
+    if (B > 0)
+      tt.mel = mel_view(a.mel_blobs + static_cast<int64_t>(a.utt_mel_idx[utt]) * p.mel_blob_stride, B);
+    __syncwarp();
+    // load (reflect at edges), dither
+    float lsum = 0.0f;
+    for (int i = lane; i < W; i += 32) {
+      int64_t k = start + i;
+      while (k < 0 || k >= n) k = (k < 0) ? (-k - 1) : (2 * n - 1 - k);
+      float v = a.pcm_f32 ? a.pcm_f32[utt_off + k] : static_cast<float>(a.pcm[utt_off + k]);
+      if (p.fo.dither != 0.0f) {
+        float g0, g1;
+        gauss_pair(a.seed, static_cast<uint64_t>(row), i >> 1, &g0, &g1);
+        v = fmaf(p.fo.dither, (i & 1) ? g1 : g0, v);
+      }
+      buf_a[i] = v;
+      lsum += v;
+    }
+    float mean = 0.0f;
+    if (p.fo.remove_dc_offset) mean = __fdiv_rn(group_sum<32>(lsum), static_cast<float>(W));
+    __syncwarp();
+    float log_energy = 0.0f;
+    {
+      float e = 0.0f;
+      for (int i = lane; i < W; i += 32) {
+        const float v = buf_a[i] - mean;
+        buf_a[i] = v;
+        e = fmaf(v, v, e);
+      }
+      if (p.need_raw_energy) log_energy = logf(fmaxf(group_sum<32>(e), p.eps_energy));
+    }
+    __syncwarp();
+    // pre-emphasis + window -> buf_b (bit-reversed when a pow2 FFT follows)
+    const float c = p.fo.preemph_coeff;
+    float e_post = 0.0f;
+    double e64 = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      float v = 0.0f;
+      if (i < W) {
+        const float prev = buf_a[i > 0 ? i - 1 : 0];
+        v = buf_a[i];
+        if (c != 0.0f) v = fmaf(-c, prev, v);
+        v *= p.t.window[i];
+      }
+      e_post = fmaf(v, v, e_post);
+      e64 += static_cast<double>(v) * v;
+      const int dst = (a.log2n >= 0) ? static_cast<int>(__brev(static_cast<unsigned>(i)) >> (32 - a.log2n)) : i;
+      buf_b[dst] = v;
+    }
+    if (xo.kind == SNB_FEAT_ENERGY) {
+      e64 = group_sum_f64<32>(e64);
+      if (lane == 0)
+        reinterpret_cast<double *>(a.out)[row * a.ld_out] = compress_energy(e64, xo.energy_compression);
+      continue;
+    }
+    if (p.need_post_energy) log_energy = logf(fmaxf(group_sum<32>(e_post), p.eps_energy));
+    __syncwarp();
+    float *P;
+    if (a.log2n >= 0) {
+      // in-place radix-2 DIT: real part buf_b, imaginary part buf_a
+      for (int i = lane; i < N; i += 32) buf_a[i] = 0.0f;
+      __syncwarp();
+      for (int h = 1; h < N; h <<= 1) {
+        const int tstride = N / (2 * h);
+        for (int j = lane; j < half; j += 32) {
+          const int pos = j & (h - 1);
+          const int i0 = ((j - pos) << 1) + pos, i1 = i0 + h;
+          const float2 w = p.t.tw_dft[pos * tstride];
+          const float ur = buf_b[i0], ui = buf_a[i0];
+          const float xr = buf_b[i1], xi = buf_a[i1];
+          const float vr = xr * w.x - xi * w.y, vi = xr * w.y + xi * w.x;
+          buf_b[i0] = ur + vr; buf_a[i0] = ui + vi;
+          buf_b[i1] = ur - vr; buf_a[i1] = ui - vi;
+        }
+        __syncwarp();
+      }
+      for (int k = lane; k <= half; k += 32) {
+        const float r = buf_b[k], i = buf_a[k];
+        buf_b[k] = (k == 0 || k == half) ? r * r : r * r + i * i;
+      }
+      P = buf_b;
+    } else {
+      // direct DFT (round_to_power_of_two=False, Kaldi's generic RealFft)
+      for (int k = lane; k <= half; k += 32) {
+        float sr = 0.0f, si = 0.0f;
+        int idx = 0;
+        for (int t = 0; t < N; ++t) {
+          const float2 w = p.t.tw_dft[idx];
+          const float v = buf_b[t];
+          sr = fmaf(v, w.x, sr);
+          si = fmaf(v, w.y, si);
+          idx += k;
+          if (idx >= N) idx -= N;
+        }
+        buf_a[k] = (k == 0 || 2 * k == N) ? sr * sr : sr * sr + si * si;
+      }
+      P = buf_a;
+    }
+    __syncwarp();
+    float *out_row = reinterpret_cast<float *>(a.out) + row * a.ld_out;
+    feature_tail<32>(p, tt, P, scratch, log_energy, out_row, true, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host: plan
+// ---------------------------------------------------------------------------
+static int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+static void fast_layout(const snb_plan *plan, FastSmemLayout *sm) {
+  const FeatParams &p = plan->params;
+  const snb_feat_opts &xo = p.xo;
+  int off = 0;
+  sm->window = off; off += 512 * 4;
+  sm->tw1 = off; off += 256 * 8;
+  sm->tw2 = off; off += 128 * 8;
+  sm->dct = off; off += align_up((xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * p.B : 0) * 4, 16);
+  sm->lifter = off; off += align_up(xo.num_ceps * 4, 16);
+  sm->idft = off; off += align_up((xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0) * 4, 16);
+  sm->mel = off; off += align_up(p.mel_blob_stride * 4, 16);
+  sm->span_cap = align_up((plan->tile_frames - 1) * p.S + p.W + 16, 8);
+  sm->pcm = off; off += align_up(sm->span_cap * 2, 16);
+  sm->grp_floats = align_up(std::max(16 * kXStride * 2, 272 + p.B + 2 + xo.lpc_order + 2), 4);
+  sm->grp = off; off += kFastGroups * sm->grp_floats * 4;
+  sm->bar = off; off += 16;
+  sm->total = off;
+}
+
+int feature_plan_finalize(snb_plan *plan) {
+  FeatParams &p = plan->params;
+  const snb_feat_opts &xo = p.xo;
+  plan->fast_path = false;
+  const int group_need = (xo.kind == SNB_FEAT_PLP) ? xo.lpc_order + 1 : 1;
+  if (p.N == 512 && p.W > 256 && p.B <= 200 && group_need <= 16) {
+    // tile so that the staged span stays small (<= 24 KB of int16)
+    int t = 32;
+    while (t > 1 && ((t - 1) * p.S + p.W + 16) * 2 > 24 * 1024) t /= 2;
+    plan->tile_frames = t;
+    FastSmemLayout sm;
+    fast_layout(plan, &sm);
+    if (sm.total <= 200 * 1024) {
+      plan->fast_path = true;
+      plan->smem_bytes = sm.total;
+      cudaError_t e = cudaFuncSetAttribute(fused_features_512_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
+      if (e != cudaSuccess) {
+        // no usable device (e.g. symbol-export tests on a CPU box): keep the
+        // plan, the error will surface at the first compute call
+        cudaGetLastError();
+      }
+      return SNB_OK;
+    }
+  }
+  if (group_need > 32)
+    return set_error(SNB_ERR_UNSUPPORTED, "lpc_order > 31 is not supported");
+  if (p.N > 8192)
+    return set_error(SNB_ERR_UNSUPPORTED, "frame length above 8192 samples is not supported");
+  plan->tile_frames = 1;
+  const int tables = (xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * p.B : 0) + xo.num_ceps +
+                     (xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0);
+  const int warp_floats = 2 * p.N + p.B + 2 + xo.lpc_order + 2 + 8;
+  plan->smem_bytes = static_cast<size_t>(align_up(tables, 4) + kGenWarps * align_up(warp_floats, 4)) * 4;
+  if (plan->smem_bytes > 220 * 1024)
+    return set_error(SNB_ERR_UNSUPPORTED, "options need too much shared memory");
+  cudaError_t e = cudaFuncSetAttribute(generic_features_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(plan->smem_bytes));
+  if (e != cudaSuccess) cudaGetLastError();
+  return SNB_OK;
+}
+
+// builds the int32 mel blob for one VTLN warp (cached in the plan)
+static int get_mel_blob(const snb_plan *plan, float warp, const std::vector<int32_t> **out) {
+  uint32_t key;
+  std::memcpy(&key, &warp, 4);
+  std::lock_guard<std::mutex> lock(plan->mu);
+  auto it = plan->mel_blobs.find(key);
+  if (it == plan->mel_blobs.end()) {
+    MelBanksHost mb;
+    int rc = build_mel_banks(plan->fo, plan->mo, warp, &mb);
+    if (rc != SNB_OK) return rc;
+    const FeatParams &p = plan->params;
+    if (static_cast<int>(mb.weights.size()) > p.mel_wcap)
+      return set_error(SNB_ERR_UNSUPPORTED, "mel weights overflow (%zu > %d)", mb.weights.size(), p.mel_wcap);
+    std::vector<int32_t> blob(p.mel_blob_stride, 0);
+    const int B = p.B;
+    std::vector<float> loud;
+    build_equal_loudness(mb.center_freqs, &loud);
+    for (int b = 0; b < B; ++b) {
+      blob[b] = mb.first[b];
+      blob[B + b] = mb.size[b];
+      blob[2 * B + b] = mb.offset[b];
+      std::memcpy(&blob[3 * B + b], &loud[b], 4);
+    }
+    std::memcpy(&blob[4 * B], mb.weights.data(), mb.weights.size() * 4);
+    it = plan->mel_blobs.emplace(key, std::move(blob)).first;
+  }
+  *out = &it->second;
+  return SNB_OK;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_opts *mo,
+                                       const snb_feat_opts *xo, snb_plan **out) {
+  if (!fo || !xo || !out) return set_error(SNB_ERR_VALUE, "null argument");
+  *out = nullptr;
+  const int kind = xo->kind;
+  if (kind < SNB_FEAT_SPECTROGRAM || kind > SNB_FEAT_ENERGY)
+    return set_error(SNB_ERR_VALUE, "unknown feature kind %d", kind);
+  const bool needs_mel = kind == SNB_FEAT_FBANK || kind == SNB_FEAT_MFCC || kind == SNB_FEAT_PLP;
+  if (needs_mel && !mo) return set_error(SNB_ERR_VALUE, "mel options required");
+  snb_plan *plan = new snb_plan();
+  plan->kind = 0;
+  plan->fo = *fo;
+  plan->xo = *xo;
+  if (needs_mel) plan->mo = *mo;
+  plan->has_mel = needs_mel;
+  if (kind == SNB_FEAT_ENERGY && xo->raw_energy) {
+    // energy.py:148-151: raw energy = no pre-emphasis, rectangular window
+    plan->fo.preemph_coeff = 0.0f;
+    plan->fo.window_type = SNB_WIN_RECTANGULAR;
+  }
+  cudaGetDevice(&plan->device);
+  cudaGetLastError();
+  FeatParams &p = plan->params;
+  std::memset(&p, 0, sizeof(p));
+  p.fo = plan->fo;
+  p.xo = *xo;
+  p.W = window_size(plan->fo);
+  p.S = window_shift(plan->fo);
+  p.N = padded_window_size(plan->fo);
+  int rc = SNB_OK;
+  auto fail = [&](int code) { delete plan; return code; };
+  if (p.W <= 0 || p.S <= 0)
+    return fail(set_error(SNB_ERR_OPTION, "frame length/shift too small for the sample rate"));
+  if (p.W < 2) return fail(set_error(SNB_ERR_OPTION, "window of less than 2 samples"));
+  p.B = needs_mel ? mo->num_bins : 0;
+  switch (kind) {
+    case SNB_FEAT_SPECTROGRAM:
+      p.dim = p.N / 2 + 1;
+      p.need_raw_energy = xo->raw_energy != 0;
+      p.need_post_energy = !xo->raw_energy;
+      break;
+    case SNB_FEAT_FBANK:
+      p.dim = p.B + (xo->use_energy ? 1 : 0);
+      break;
+    case SNB_FEAT_MFCC:
+      if (xo->num_ceps <= 0 || xo->num_ceps > p.B)
+        return fail(set_error(SNB_ERR_OPTION, "num-ceps cannot be larger than num-mel-bins: %d vs %d",
+                              xo->num_ceps, p.B));
+      p.dim = xo->num_ceps;
+      break;
+    case SNB_FEAT_PLP:
+      if (xo->num_ceps <= 0 || xo->num_ceps > xo->lpc_order + 1)
+        return fail(set_error(SNB_ERR_OPTION, "num_ceps must be in [1, lpc_order+1]"));
+      if (xo->rasta)
+        return fail(set_error(SNB_ERR_UNSUPPORTED, "rasta filtering is not implemented on the GPU path yet"));
+      p.dim = xo->num_ceps;
+      break;
+    default:
+      p.dim = 1;
+  }
+  if (kind != SNB_FEAT_SPECTROGRAM && kind != SNB_FEAT_ENERGY) {
+    p.need_raw_energy = xo->use_energy && xo->raw_energy;
+    p.need_post_energy = xo->use_energy && !xo->raw_energy;
+  }
+  p.log_energy_floor = xo->energy_floor > 0.0f ? logf(xo->energy_floor) : 0.0f;
+  p.eps_energy = (kind == SNB_FEAT_PLP) ? 2.220446049250313e-16f : FLT_EPSILON;
+  if (p.N % 2 != 0 && kind != SNB_FEAT_ENERGY)
+    return fail(set_error(SNB_ERR_OPTION, "padded window size must be even, it is %d", p.N));
+  // validate the mel options now (KALDI_ERR at construction of the computer)
+  if (needs_mel) {
+    p.mel_wcap = 2 * (p.N / 2) + 2 * p.B + 8;
+    p.mel_blob_stride = 4 * p.B + p.mel_wcap;
+    const std::vector<int32_t> *blob;
+    rc = get_mel_blob(plan, 1.0f, &blob);
+    if (rc != SNB_OK) return fail(rc);
+  }
+  // ---- fixed tables: window | tw_half | tw_full | dct | lifter | idft | tw_dft
+  std::vector<float> win;
+  window_function(plan->fo, &win);
+  const int half = p.N / 2;
+  std::vector<float> host;
+  auto append = [&](const std::vector<float> &v) {
+    size_t off = host.size();
+    host.insert(host.end(), v.begin(), v.end());
+    while (host.size() % 4) host.push_back(0.0f);
+    return off;
+  };
+  const double two_pi = 6.283185307179586476925286766559005;
+  std::vector<float> tw_half(2 * std::max(half, 1)), tw_full(2 * std::max(half, 1)), tw_dft(2 * p.N);
+  for (int m = 0; m < half; ++m) {
+    tw_half[2 * m] = static_cast<float>(std::cos(two_pi * m / half));
+    tw_half[2 * m + 1] = static_cast<float>(-std::sin(two_pi * m / half));
+    tw_full[2 * m] = static_cast<float>(std::cos(two_pi * m / p.N));
+    tw_full[2 * m + 1] = static_cast<float>(-std::sin(two_pi * m / p.N));
+  }
+  for (int m = 0; m < p.N; ++m) {
+    tw_dft[2 * m] = static_cast<float>(std::cos(two_pi * m / p.N));
+    tw_dft[2 * m + 1] = static_cast<float>(-std::sin(two_pi * m / p.N));
+  }
+  std::vector<float> dct, lifter, idft;
+  if (kind == SNB_FEAT_MFCC) build_dct(xo->num_ceps, p.B, &dct);
+  if (kind == SNB_FEAT_MFCC || kind == SNB_FEAT_PLP) build_lifter(xo->num_ceps, xo->cepstral_lifter, &lifter);
+  if (kind == SNB_FEAT_PLP) build_idft_bases(xo->lpc_order + 1, p.B + 2, &idft);
+  const size_t o_win = append(win), o_th = append(tw_half), o_tf = append(tw_full),
+               o_dct = append(dct), o_lift = append(lifter), o_idft = append(idft),
+               o_dft = append(tw_dft);
+  float *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    // Without a usable GPU the product cannot run: fail loudly.
+    cudaGetLastError();
+    if (d) cudaFree(d);
+    return fail(set_error(SNB_ERR_CUDA, "cannot upload plan tables: %s", cudaGetErrorString(e)));
+  }
+  plan->d_tables = d;
+  p.t.window = d + o_win;
+  p.t.tw_half = reinterpret_cast<const float2 *>(d + o_th);
+  p.t.tw_full = reinterpret_cast<const float2 *>(d + o_tf);
+  p.t.dct = d + o_dct;
+  p.t.lifter = d + o_lift;
+  p.t.idft = d + o_idft;
+  p.t.tw_dft = reinterpret_cast<const float2 *>(d + o_dft);
+  rc = feature_plan_finalize(plan);
+  if (rc != SNB_OK) {
+    cudaFree(d);
+    return fail(rc);
+  }
+  *out = plan;
+  return SNB_OK;
+}
+
+extern "C" void snb_plan_destroy(snb_plan *plan) {
+  if (!plan) return;
+  if (plan->d_tables) cudaFree(plan->d_tables);
+  if (plan->kind == 1) pitch_plan_free(plan);
+  delete plan;
+}
+
+extern "C" int32_t snb_plan_dim(const snb_plan *plan) {
+  return plan->kind == 0 ? plan->params.dim : 2;
+}
+extern "C" int32_t snb_plan_uses_fast_path(const snb_plan *plan) { return plan->fast_path ? 1 : 0; }
+
+// ---------------------------------------------------------------------------
+// host: batch
+// ---------------------------------------------------------------------------
+extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begin,
+                                const int64_t *sample_len, int64_t nutts, const float *vtln_warps,
+                                snb_batch **out) {
+  if (!plan || !out || nutts < 0 || (nutts > 0 && (!sample_begin || !sample_len)))
+    return set_error(SNB_ERR_VALUE, "bad argument");
+  *out = nullptr;
+  snb_batch *b = new snb_batch();
+  b->plan = plan;
+  b->nutts = nutts;
+  b->sample_begin.assign(sample_begin, sample_begin + nutts);
+  b->sample_len.assign(sample_len, sample_len + nutts);
+  b->total_samples = 0;
+  b->frame_offsets.assign(nutts + 1, 0);
+  auto fail = [&](int code) { snb_batch_destroy(b); return code; };
+  for (int64_t u = 0; u < nutts; ++u) {
+    const int64_t n = sample_len[u];
+    if (n < 0 || sample_begin[u] < 0) return fail(set_error(SNB_ERR_VALUE, "negative sample begin/length"));
+    b->total_samples = std::max(b->total_samples, sample_begin[u] + n);
+    int64_t nf;
+    if (plan->kind == 0) nf = num_frames(n, plan->fo);
+    else nf = snb_pitch_num_frames(n, &plan->po);
+    if (nf < 0) nf = 0;
+    if (nf > 0x7fffffff) return fail(set_error(SNB_ERR_VALUE, "utterance too long"));
+    b->frame_offsets[u + 1] = b->frame_offsets[u] + nf;
+  }
+  b->total_frames = b->frame_offsets[nutts];
+  cudaError_t e = cudaMalloc(&b->d_sample_begin, (nutts + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_sample_len, (nutts + 1) * sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_frame_offsets, (nutts + 1) * sizeof(int64_t));
+  if (e == cudaSuccess && nutts > 0)
+    e = cudaMemcpy(b->d_sample_begin, b->sample_begin.data(), nutts * sizeof(int64_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nutts > 0)
+    e = cudaMemcpy(b->d_sample_len, b->sample_len.data(), nutts * sizeof(int64_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(b->d_frame_offsets, b->frame_offsets.data(), (nutts + 1) * sizeof(int64_t),
+                   cudaMemcpyHostToDevice);
+  if (e != cudaSuccess)
+    return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
+  if (plan->kind == 1) {
+    int rc = pitch_batch_init(plan, b);
+    if (rc != SNB_OK) return fail(rc);
+    *out = b;
+    return SNB_OK;
+  }
+  // ---- mel blobs for the distinct VTLN warps of this batch ----
+  std::vector<int32_t> utt_mel(nutts, 0);
+  std::vector<int32_t> blobs;
+  if (plan->has_mel) {
+    std::map<uint32_t, int32_t> index;
+    for (int64_t u = 0; u < nutts; ++u) {
+      const float w = vtln_warps ? vtln_warps[u] : 1.0f;
+      uint32_t key;
+      std::memcpy(&key, &w, 4);
+      auto it = index.find(key);
+      if (it == index.end()) {
+        const std::vector<int32_t> *blob;
+        int rc = get_mel_blob(plan, w, &blob);
+        if (rc != SNB_OK) return fail(rc);
+        it = index.emplace(key, static_cast<int32_t>(index.size())).first;
+        blobs.insert(blobs.end(), blob->begin(), blob->end());
+      }
+      utt_mel[u] = it->second;
+    }
+    b->nblobs = static_cast<int32_t>(index.size());
+    if (nutts == 0) {
+      const std::vector<int32_t> *blob;
+      get_mel_blob(plan, 1.0f, &blob);
+      blobs = *blob;
+      b->nblobs = 1;
+    }
+    e = cudaMalloc(&b->d_mel_blobs, blobs.size() * sizeof(int32_t));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(b->d_mel_blobs, blobs.data(), blobs.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+      return fail(set_error(SNB_ERR_CUDA, "mel upload failed: %s", cudaGetErrorString(e)));
+  }
+  // ---- tile table (fast path) or per-utterance mel index (generic) ----
+  if (plan->fast_path) {
+    std::vector<TileDesc> tiles;
+    const int T = plan->tile_frames;
+    for (int64_t u = 0; u < nutts; ++u) {
+      const int64_t nf = b->frame_offsets[u + 1] - b->frame_offsets[u];
+      for (int64_t f0 = 0; f0 < nf; f0 += T) {
+        TileDesc td;
+        td.utt = static_cast<int32_t>(u);
+        td.f0 = static_cast<int32_t>(f0);
+        td.nf = static_cast<int32_t>(std::min<int64_t>(T, nf - f0));
+        td.mel_idx = utt_mel[u];
+        tiles.push_back(td);
+      }
+    }
+    b->ntiles = static_cast<int64_t>(tiles.size());
+    if (b->ntiles > 0) {
+      e = cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc));
+      if (e == cudaSuccess)
+        e = cudaMemcpy(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess)
+        return fail(set_error(SNB_ERR_CUDA, "tile upload failed: %s", cudaGetErrorString(e)));
+    }
+  } else {
+    // generic kernel: per-utterance mel index, stored in the d_tiles slot
+    if (nutts > 0) {
+      e = cudaMalloc(&b->d_tiles, nutts * sizeof(int32_t));
+      if (e == cudaSuccess)
+        e = cudaMemcpy(b->d_tiles, utt_mel.data(), nutts * sizeof(int32_t), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess)
+        return fail(set_error(SNB_ERR_CUDA, "index upload failed: %s", cudaGetErrorString(e)));
+    }
+  }
+  *out = b;
+  return SNB_OK;
+}
+
+extern "C" void snb_batch_destroy(snb_batch *b) {
+  if (!b) return;
+  if (b->d_sample_begin) cudaFree(b->d_sample_begin);
+  if (b->d_sample_len) cudaFree(b->d_sample_len);
+  if (b->d_frame_offsets) cudaFree(b->d_frame_offsets);
+  if (b->d_tiles) cudaFree(b->d_tiles);
+  if (b->d_mel_blobs) cudaFree(b->d_mel_blobs);
+  if (b->d_down_offsets) cudaFree(b->d_down_offsets);
+  delete b;
+}
+extern "C" int64_t snb_batch_num_utts(const snb_batch *b) { return b->nutts; }
+extern "C" int64_t snb_batch_total_frames(const snb_batch *b) { return b->total_frames; }
+extern "C" const int64_t *snb_batch_frame_offsets(const snb_batch *b) { return b->frame_offsets.data(); }
+extern "C" const int64_t *snb_batch_frame_offsets_device(const snb_batch *b) { return b->d_frame_offsets; }
+
+// ---------------------------------------------------------------------------
+// host: launch
+// ---------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
+                                 const float *d_wave, int64_t capacity, uint64_t seed, void *d_out,
+                                 int64_t ld_out, void *stream_) {
+  if (!plan || !batch || plan->kind != 0 || batch->plan != plan)
+    return set_error(SNB_ERR_VALUE, "plan/batch mismatch");
+  if (batch->total_frames == 0) return SNB_OK;
+  if ((!d_pcm && !d_wave) || !d_out) return set_error(SNB_ERR_VALUE, "null device buffer");
+  if (capacity < batch->total_samples)
+    return set_error(SNB_ERR_VALUE, "pcm buffer smaller than the batch (%lld < %lld samples)",
+                     (long long)capacity, (long long)batch->total_samples);
+  const FeatParams &p = plan->params;
+  if (ld_out < p.dim) return set_error(SNB_ERR_VALUE, "ld_out %lld < dim %d", (long long)ld_out, p.dim);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (plan->fast_path && !d_wave) {
+    FastArgs a;
+    a.p = p;
+    fast_layout(plan, &a.sm);
+    a.tiles = batch->d_tiles;
+    a.ntiles = batch->ntiles;
+    a.sample_begin = batch->d_sample_begin;
+    a.sample_len = batch->d_sample_len;
+    a.frame_offsets = batch->d_frame_offsets;
+    a.mel_blobs = batch->d_mel_blobs;
+    a.pcm = d_pcm;
+    a.total_samples = capacity;
+    a.out = d_out;
+    a.ld_out = ld_out;
+    a.seed = seed;
+    static const bool no_tma = getenv("SNB_NO_TMA") != nullptr;
+    a.use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(d_pcm) % 16 == 0)) ? 1 : 0;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_features_512_kernel, kFastThreads,
+                                                  a.sm.total);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = std::min<int64_t>(batch->ntiles, static_cast<int64_t>(num_sms()) * per_sm);
+    fused_features_512_kernel<<<static_cast<unsigned>(grid), kFastThreads, a.sm.total, stream>>>(a);
+    SNB_LAUNCH_CHECK();
+    return SNB_OK;
+  }
+  if (d_wave && p.B > 0)
+    return set_error(SNB_ERR_UNSUPPORTED, "float32 input is only supported for the energy kind");
+  GenArgs g;
+  g.p = p;
+  g.log2n = -1;
+  if ((p.N & (p.N - 1)) == 0) {
+    g.log2n = 0;
+    while ((1 << g.log2n) < p.N) ++g.log2n;
+  }
+  const snb_feat_opts &xo = p.xo;
+  const int tables = (xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * p.B : 0) + xo.num_ceps +
+                     (xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0);
+  g.tables_floats = align_up(tables, 4);
+  g.warp_floats = align_up(2 * p.N + p.B + 2 + xo.lpc_order + 2 + 8, 4);
+  g.sample_begin = batch->d_sample_begin;
+  g.sample_len = batch->d_sample_len;
+  g.frame_offsets = batch->d_frame_offsets;
+  g.utt_mel_idx = plan->fast_path ? nullptr : reinterpret_cast<const int32_t *>(batch->d_tiles);
+  g.mel_blobs = batch->d_mel_blobs;
+  g.pcm = d_pcm;
+  g.pcm_f32 = d_wave;
+  g.nutts = batch->nutts;
+  g.total_frames = batch->total_frames;
+  g.out = d_out;
+  g.ld_out = ld_out;
+  g.seed = seed;
+  size_t smem = plan->smem_bytes;
+  if (plan->fast_path) {
+    // float input on a plan whose batches are tiled for the fast path (energy)
+    smem = static_cast<size_t>(g.tables_floats + kGenWarps * g.warp_floats) * 4;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(generic_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem));
+  }
+  const int64_t want = (batch->total_frames + kGenWarps - 1) / kGenWarps;
+  const int64_t grid = std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 8);
+  generic_features_kernel<<<static_cast<unsigned>(grid), kGenWarps * 32, smem, stream>>>(g);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_compute_features(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
+                                    int64_t pcm_capacity, uint64_t seed, void *d_out, int64_t ld_out,
+                                    void *stream) {
+  return compute_features_impl(plan, batch, d_pcm, nullptr, pcm_capacity, seed, d_out, ld_out, stream);
+}
+
+extern "C" int snb_compute_features_f32(const snb_plan *plan, const snb_batch *batch, const float *d_wave,
+                                        int64_t capacity, uint64_t seed, void *d_out, int64_t ld_out,
+                                        void *stream) {
+  return compute_features_impl(plan, batch, nullptr, d_wave, capacity, seed, d_out, ld_out, stream);
+}

@@ -1,0 +1,794 @@
+// pitch.cu -- Kaldi pitch extraction and post-processing for ragged batches.
+//
+// Replaces kaldi.feat.pitch.compute_kaldi_pitch / process_pitch
+// (shennong/processor/pitch_kaldi.py:296-299, 535-537), i.e. Kaldi's
+// pitch-functions.cc + resample.cc in OFFLINE use: one AcceptWaveform() with
+// the resampler unflushed followed by InputFinished().
+//
+//   k1  resample_kernel      16k -> 4k windowed-sinc (LinearResample), one
+//                            thread per output sample, all utterances at once
+//   k2  pitch_track_kernel   one CTA per utterance, sequential over frames:
+//                            NCCF at the integer lags, sinc-upsample to the
+//                            log-spaced lags (ArbitraryResample), one exact
+//                            Viterbi step (min-plus over all states), back-
+//                            pointers to a per-CTA scratch; then backtrace and
+//                            the (NCCF, pitch) rows
+//   k3  process_pitch_kernel POV / normalised log-pitch / delta / raw log-pitch
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "device_utils.cuh"
+#include "snb_internal.h"
+
+namespace snb {
+
+constexpr int kPitchThreads = 256;
+constexpr int kMaxStatesPerThread = 8;
+
+struct PitchTables {
+  // host copies
+  int32_t rate_in, rate_out, in_unit, out_unit;
+  int32_t first_lag, last_lag, nmeas, nstates;
+  int32_t shift, basic_len, full_len;
+  int32_t down_nw_max, up_nw_max;
+  std::vector<int32_t> down_first, down_nw;     // [out_unit]
+  std::vector<float> down_w;                    // [out_unit, down_nw_max]
+  std::vector<float> lags, pen;                 // [nstates]
+  std::vector<int32_t> up_first, up_nw;         // [nstates]
+  std::vector<float> up_w;                      // [nstates, up_nw_max]
+  // device copies (one allocation)
+  void *d_blob = nullptr;
+  const int32_t *d_down_first, *d_down_nw, *d_up_first, *d_up_nw;
+  const float *d_down_w, *d_lags, *d_pen, *d_up_w;
+};
+
+static int32_t gcd_i32(int32_t a, int32_t b) {
+  while (b) { const int32_t t = a % b; a = b; b = t; }
+  return a;
+}
+
+// LinearResample::FilterFunc / ArbitraryResample::FilterFunc
+static float sinc_filter(float t, float cutoff, int32_t num_zeros) {
+  const double two_pi = 6.283185307179586476925286766559005, pi = 3.1415926535897932384626433832795;
+  float window = 0.0f, filter;
+  if (std::fabs(static_cast<double>(t)) < num_zeros / (2.0 * cutoff))
+    window = static_cast<float>(0.5 * (1 + std::cos(two_pi * cutoff / num_zeros * t)));
+  if (t != 0.0f) filter = static_cast<float>(std::sin(two_pi * cutoff * t) / (pi * t));
+  else filter = static_cast<float>(2.0 * cutoff);
+  return filter * window;
+}
+
+static int64_t resample_num_out(int64_t n_in, const snb_pitch_opts &o, bool flush) {
+  const int32_t rate_in = static_cast<int32_t>(o.samp_freq), rate_out = static_cast<int32_t>(o.resample_freq);
+  const int32_t base = gcd_i32(rate_in, rate_out);
+  const int64_t tick_freq = static_cast<int64_t>(rate_in) / base * rate_out;
+  int64_t interval = n_in * (tick_freq / rate_in);
+  if (!flush) {
+    const float window_width = static_cast<float>(o.lowpass_filter_width / (2.0 * o.lowpass_cutoff));
+    interval -= static_cast<int32_t>(std::floor(static_cast<double>(window_width * static_cast<float>(tick_freq))));
+  }
+  if (interval <= 0) return 0;
+  const int64_t per_out = tick_freq / rate_out;
+  int64_t last = interval / per_out;
+  if (last * per_out == interval) --last;
+  return last + 1;
+}
+
+static void lag_range(const snb_pitch_opts &o, int32_t *first, int32_t *last) {
+  const double outer_min = 1.0 / o.max_f0 - o.upsample_filter_width / (2.0 * o.resample_freq);
+  const double outer_max = 1.0 / o.min_f0 + o.upsample_filter_width / (2.0 * o.resample_freq);
+  *first = static_cast<int32_t>(std::ceil(o.resample_freq * outer_min));
+  *last = static_cast<int32_t>(std::floor(o.resample_freq * outer_max));
+}
+
+static int32_t nccf_win_size(const snb_pitch_opts &o) {
+  return static_cast<int32_t>(static_cast<double>(o.resample_freq) * o.frame_length_ms / 1000.0);
+}
+static int32_t nccf_win_shift(const snb_pitch_opts &o) {
+  return static_cast<int32_t>(static_cast<double>(o.resample_freq) * o.frame_shift_ms / 1000.0);
+}
+
+static int64_t frames_available(int64_t n_down, const snb_pitch_opts &o, int32_t last_lag, bool finished) {
+  const int32_t shift = nccf_win_shift(o);
+  int32_t length = nccf_win_size(o);
+  if (!finished) length += last_lag;
+  if (shift <= 0 || n_down < length) return 0;
+  if (!o.snip_edges) {
+    if (finished) return static_cast<int64_t>(static_cast<float>(n_down) * 1.0f / static_cast<float>(shift) + 0.5f);
+    return static_cast<int64_t>(static_cast<float>(n_down - length / 2) * 1.0f / static_cast<float>(shift) + 0.5f);
+  }
+  return (n_down - length) / shift + 1;
+}
+
+static bool pitch_opts_valid(const snb_pitch_opts &o) {
+  return o.samp_freq > 0 && o.resample_freq > 0 && o.min_f0 > 0 && o.max_f0 > o.min_f0 &&
+         o.lowpass_cutoff > 0 && o.delta_pitch > 0 && o.frame_shift_ms > 0 && o.frame_length_ms > 0 &&
+         o.lowpass_filter_width > 0 && o.upsample_filter_width > 0 &&
+         o.resample_freq > 2 * o.lowpass_cutoff * 0.999f && o.samp_freq >= o.resample_freq;
+}
+
+int pitch_plan_init(snb_plan *plan) {
+  const snb_pitch_opts &o = plan->po;
+  if (!pitch_opts_valid(o)) return set_error(SNB_ERR_OPTION, "invalid pitch extraction options");
+  PitchTables *t = new PitchTables();
+  plan->pitch = t;
+  t->rate_in = static_cast<int32_t>(o.samp_freq);
+  t->rate_out = static_cast<int32_t>(o.resample_freq);
+  const int32_t base = gcd_i32(t->rate_in, t->rate_out);
+  t->in_unit = t->rate_in / base;
+  t->out_unit = t->rate_out / base;
+  // --- LinearResample::SetIndexesAndWeights ---
+  const double window_width = o.lowpass_filter_width / (2.0 * o.lowpass_cutoff);
+  t->down_first.resize(t->out_unit);
+  t->down_nw.resize(t->out_unit);
+  std::vector<std::vector<float>> dw(t->out_unit);
+  t->down_nw_max = 0;
+  for (int32_t i = 0; i < t->out_unit; ++i) {
+    const double output_t = i / static_cast<double>(t->rate_out);
+    const int32_t min_idx = static_cast<int32_t>(std::ceil((output_t - window_width) * t->rate_in));
+    const int32_t max_idx = static_cast<int32_t>(std::floor((output_t + window_width) * t->rate_in));
+    t->down_first[i] = min_idx;
+    t->down_nw[i] = max_idx - min_idx + 1;
+    for (int32_t j = 0; j < t->down_nw[i]; ++j) {
+      const double delta_t = (min_idx + j) / static_cast<double>(t->rate_in) - output_t;
+      dw[i].push_back(sinc_filter(static_cast<float>(delta_t), o.lowpass_cutoff, o.lowpass_filter_width) /
+                      static_cast<float>(t->rate_in));
+    }
+    t->down_nw_max = std::max(t->down_nw_max, t->down_nw[i]);
+  }
+  t->down_w.assign(static_cast<size_t>(t->out_unit) * t->down_nw_max, 0.0f);
+  for (int32_t i = 0; i < t->out_unit; ++i)
+    std::copy(dw[i].begin(), dw[i].end(), t->down_w.begin() + static_cast<size_t>(i) * t->down_nw_max);
+  // --- lags (SelectLags) ---
+  lag_range(o, &t->first_lag, &t->last_lag);
+  t->nmeas = t->last_lag + 1 - t->first_lag;
+  {
+    const float min_lag = static_cast<float>(1.0 / o.max_f0), max_lag = static_cast<float>(1.0 / o.min_f0);
+    for (float lag = min_lag; lag <= max_lag; lag = static_cast<float>(lag * (1.0 + o.delta_pitch)))
+      t->lags.push_back(lag);
+  }
+  t->nstates = static_cast<int32_t>(t->lags.size());
+  t->shift = nccf_win_shift(o);
+  t->basic_len = nccf_win_size(o);
+  t->full_len = t->basic_len + t->last_lag;
+  if (t->nmeas <= 0 || t->nstates <= 0 || t->shift <= 0 || t->basic_len <= 0)
+    return set_error(SNB_ERR_OPTION, "invalid pitch extraction options");
+  if (t->nstates > kPitchThreads * kMaxStatesPerThread || t->full_len > 4096 || t->nmeas > 1024)
+    return set_error(SNB_ERR_UNSUPPORTED, "pitch options outside the GPU path limits");
+  // --- ArbitraryResample (float arithmetic as in resample.cc) ---
+  const float up_cutoff = o.resample_freq * 0.5f;
+  const float filter_width = static_cast<float>(o.upsample_filter_width / (2.0 * up_cutoff));
+  t->up_first.resize(t->nstates);
+  t->up_nw.resize(t->nstates);
+  std::vector<std::vector<float>> uw(t->nstates);
+  t->up_nw_max = 1;
+  for (int32_t i = 0; i < t->nstates; ++i) {
+    const float tt = t->lags[i] + (-static_cast<float>(t->first_lag) / o.resample_freq);
+    int32_t imin = static_cast<int32_t>(std::ceil(static_cast<double>(o.resample_freq * (tt - filter_width))));
+    int32_t imax = static_cast<int32_t>(std::floor(static_cast<double>(o.resample_freq * (tt + filter_width))));
+    if (imin < 0) imin = 0;
+    if (imax >= t->nmeas) imax = t->nmeas - 1;
+    t->up_first[i] = imin;
+    t->up_nw[i] = std::max(0, imax - imin + 1);
+    for (int32_t j = 0; j < t->up_nw[i]; ++j) {
+      const float delta_t = tt - static_cast<float>(imin + j) / o.resample_freq;
+      uw[i].push_back(sinc_filter(delta_t, up_cutoff, o.upsample_filter_width) / o.resample_freq);
+    }
+    t->up_nw_max = std::max(t->up_nw_max, t->up_nw[i]);
+  }
+  t->up_w.assign(static_cast<size_t>(t->nstates) * t->up_nw_max, 0.0f);
+  for (int32_t i = 0; i < t->nstates; ++i)
+    std::copy(uw[i].begin(), uw[i].end(), t->up_w.begin() + static_cast<size_t>(i) * t->up_nw_max);
+  // --- Viterbi transition penalties: (i-j)^2 * inter_frame_factor ---
+  const float delta_pitch_sq = static_cast<float>(std::pow(std::log(1.0 + static_cast<double>(o.delta_pitch)), 2.0));
+  const float factor = delta_pitch_sq * o.penalty_factor;
+  t->pen.resize(t->nstates);
+  for (int32_t d = 0; d < t->nstates; ++d) t->pen[d] = static_cast<float>(d * d) * factor;
+  // --- upload ---
+  std::vector<int32_t> blob;
+  auto push_i = [&](const std::vector<int32_t> &v) { size_t off = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); while (blob.size() % 4) blob.push_back(0); return off; };
+  auto push_f = [&](const std::vector<float> &v) {
+    size_t off = blob.size();
+    blob.resize(off + v.size());
+    std::memcpy(blob.data() + off, v.data(), v.size() * 4);
+    while (blob.size() % 4) blob.push_back(0);
+    return off;
+  };
+  const size_t o1 = push_i(t->down_first), o2 = push_i(t->down_nw), o3 = push_f(t->down_w),
+               o4 = push_f(t->lags), o5 = push_f(t->pen), o6 = push_i(t->up_first), o7 = push_i(t->up_nw),
+               o8 = push_f(t->up_w);
+  int32_t *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, blob.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (d) cudaFree(d);
+    return set_error(SNB_ERR_CUDA, "cannot upload pitch tables: %s", cudaGetErrorString(e));
+  }
+  t->d_blob = d;
+  t->d_down_first = d + o1; t->d_down_nw = d + o2;
+  t->d_down_w = reinterpret_cast<const float *>(d + o3);
+  t->d_lags = reinterpret_cast<const float *>(d + o4);
+  t->d_pen = reinterpret_cast<const float *>(d + o5);
+  t->d_up_first = d + o6; t->d_up_nw = d + o7;
+  t->d_up_w = reinterpret_cast<const float *>(d + o8);
+  return SNB_OK;
+}
+
+void pitch_plan_free(snb_plan *plan) {
+  if (!plan->pitch) return;
+  if (plan->pitch->d_blob) cudaFree(plan->pitch->d_blob);
+  delete plan->pitch;
+  plan->pitch = nullptr;
+}
+
+// per-utterance phase info packed as int64 x 4: down_offset, m1, m2, end1
+int pitch_batch_init(const snb_plan *plan, snb_batch *b) {
+  const snb_pitch_opts &o = plan->po;
+  const PitchTables *t = plan->pitch;
+  std::vector<int64_t> info(static_cast<size_t>(b->nutts) * 4 + 4, 0);
+  int64_t off = 0;
+  for (int64_t u = 0; u < b->nutts; ++u) {
+    const int64_t n = b->sample_len[u];
+    const int64_t m1 = resample_num_out(n, o, false), m2 = resample_num_out(n, o, true);
+    int64_t end1 = frames_available(m1, o, t->last_lag, false);
+    const int64_t end2 = b->frame_offsets[u + 1] - b->frame_offsets[u];
+    if (end1 > end2) end1 = end2;
+    info[4 * u] = off; info[4 * u + 1] = m1; info[4 * u + 2] = m2; info[4 * u + 3] = end1;
+    off += m2;
+  }
+  info[4 * b->nutts] = off;
+  b->total_down = off;
+  b->down_offsets = info;
+  cudaError_t e = cudaMalloc(&b->d_down_offsets, info.size() * sizeof(int64_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(b->d_down_offsets, info.data(), info.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch batch upload failed: %s", cudaGetErrorString(e));
+  return SNB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k1: LinearResample::Resample for the whole batch
+// ---------------------------------------------------------------------------
+struct ResampleArgs {
+  const int16_t *pcm;
+  const int64_t *sample_begin;
+  const int64_t *sample_len;
+  const int64_t *info;          // [nutts,4] down_offset, m1, m2, end1
+  int64_t nutts, total_down;
+  int32_t in_unit, out_unit, nw_max;
+  const int32_t *first, *nw;
+  const float *w;
+  float *down;
+};
+
+__global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= a.total_down) return;
+  // utterance of this output sample (info[4u] is non-decreasing)
+  int64_t lo = 0, hi = a.nutts;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a.info[4 * mid] <= idx) lo = mid; else hi = mid;
+  }
+  const int64_t u = lo, so = idx - a.info[4 * u];
+  const int64_t in0 = a.sample_begin[u], n_in = a.sample_len[u];
+  const int64_t unit = so / a.out_unit;
+  const int32_t wrapped = static_cast<int32_t>(so - unit * a.out_unit);
+  const int64_t first_in = a.first[wrapped] + unit * a.in_unit;
+  const float *w = a.w + static_cast<int64_t>(wrapped) * a.nw_max;
+  float acc = 0.0f;
+  const int32_t nw = a.nw[wrapped];
+  for (int32_t j = 0; j < nw; ++j) {
+    const int64_t k = first_in + j;
+    if (k >= 0 && k < n_in) acc = fmaf(w[j], static_cast<float>(a.pcm[in0 + k]), acc);
+  }
+  a.down[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// k2: per-utterance NCCF + Viterbi
+// ---------------------------------------------------------------------------
+struct TrackArgs {
+  const float *down;
+  const int64_t *info;
+  const int64_t *frame_offsets;
+  int64_t nutts;
+  int32_t first_lag, nmeas, nstates, shift, basic_len, full_len, up_nw_max;
+  int32_t snip_edges;
+  float preemph, soft_min_f0, nccf_ballast;
+  const float *lags, *pen, *up_w;
+  const int32_t *up_first, *up_nw;
+  // per-CTA scratch
+  int16_t *bp;            // [grid, max_frames, nstates]
+  float *pov_raw;         // [grid, max_frames, nmeas]
+  int32_t *states;        // [grid, max_frames]
+  int64_t max_frames;
+  float *out;
+  int64_t ld_out;
+};
+
+__device__ __forceinline__ double block_sum_f64(double v, double *s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = group_sum_f64<32>(v);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kPitchThreads / 32; ++w) t += s_red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kPitchThreads) pitch_track_kernel(const TrackArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *s_win = reinterpret_cast<float *>(smem_raw);          // [full_len]
+  float *s_np = s_win + a.full_len;                             // nccf_pitch [nmeas]
+  float *s_nv = s_np + a.nmeas;                                 // nccf_pov   [nmeas]
+  float *s_prev = s_nv + a.nmeas;                               // forward cost [nstates]
+  float *s_new = s_prev + a.nstates;
+  float *s_pen = s_new + a.nstates;
+  float *s_lags = s_pen + a.nstates;
+  float *s_upw = s_lags + a.nstates;                            // [nstates, up_nw_max]
+  int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + a.nstates * a.up_nw_max);
+  int32_t *s_upn = s_upfirst + a.nstates;
+  __shared__ double s_red[kPitchThreads / 32];
+  __shared__ float s_fred[kPitchThreads / 32];
+  __shared__ int s_ired[kPitchThreads / 32];
+  __shared__ float s_scalar[4];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = a.nstates, nm = a.nmeas;
+  for (int i = tid; i < ns; i += kPitchThreads) {
+    s_pen[i] = a.pen[i];
+    s_lags[i] = a.lags[i];
+    s_upfirst[i] = a.up_first[i];
+    s_upn[i] = a.up_nw[i];
+  }
+  for (int i = tid; i < ns * a.up_nw_max; i += kPitchThreads) s_upw[i] = a.up_w[i];
+  __syncthreads();
+
+  int16_t *bp = a.bp + static_cast<int64_t>(blockIdx.x) * a.max_frames * ns;
+  float *pov_raw = a.pov_raw + static_cast<int64_t>(blockIdx.x) * a.max_frames * nm;
+  int32_t *states = a.states + static_cast<int64_t>(blockIdx.x) * a.max_frames;
+
+  for (int64_t u = blockIdx.x; u < a.nutts; u += gridDim.x) {
+    const int64_t doff = a.info[4 * u], m1 = a.info[4 * u + 1], m2 = a.info[4 * u + 2],
+                  end1 = a.info[4 * u + 3];
+    const int64_t row0 = a.frame_offsets[u], F = a.frame_offsets[u + 1] - row0;
+    if (F <= 0) continue;
+    const float *x = a.down + doff;
+    // ---- global mean-square for the ballast (double sums, two phases) ----
+    double p1 = 0.0, q1 = 0.0, p2 = 0.0, q2 = 0.0;
+    for (int64_t i = tid; i < m2; i += kPitchThreads) {
+      const double v = x[i];
+      if (i < m1) { p1 += v; q1 += v * v; } else { p2 += v; q2 += v * v; }
+    }
+    const double sum1 = block_sum_f64(p1, s_red), sq1 = block_sum_f64(q1, s_red);
+    const double sum2 = sum1 + block_sum_f64(p2, s_red), sq2 = sq1 + block_sum_f64(q2, s_red);
+    const double ms1 = m1 > 0 ? sq1 / static_cast<double>(m1) - (sum1 / static_cast<double>(m1)) * (sum1 / static_cast<double>(m1)) : 0.0;
+    const double ms2 = m2 > 0 ? sq2 / static_cast<double>(m2) - (sum2 / static_cast<double>(m2)) * (sum2 / static_cast<double>(m2)) : 0.0;
+    const float ballast1 = static_cast<float>((ms1 * a.basic_len) * (ms1 * a.basic_len) * static_cast<double>(a.nccf_ballast));
+    const float ballast2 = static_cast<float>((ms2 * a.basic_len) * (ms2 * a.basic_len) * static_cast<double>(a.nccf_ballast));
+    for (int i = tid; i < ns; i += kPitchThreads) s_prev[i] = 0.0f;
+    __syncthreads();
+
+    for (int64_t f = 0; f < F; ++f) {
+      const bool phase2 = f >= end1;
+      const int64_t avail = phase2 ? m2 : m1;
+      const float ballast = phase2 ? ballast2 : ballast1;
+      int64_t start;
+      if (a.snip_edges) start = f * a.shift;
+      else start = static_cast<int64_t>((static_cast<double>(f) + 0.5) * a.shift) - a.full_len / 2;
+      // ---- ExtractFrame (zeros outside the available signal) ----
+      for (int i = tid; i < a.full_len; i += kPitchThreads) {
+        const int64_t k = start + i;
+        s_win[i] = (k >= 0 && k < avail) ? x[k] : 0.0f;
+      }
+      __syncthreads();
+      if (a.preemph != 0.0f) {
+        // window[i] -= c * window[i-1] (original values), window[0] *= (1 - c)
+        float vals[16];
+        int cnt = 0;
+        for (int i = tid; i < a.full_len && cnt < 16; i += kPitchThreads, ++cnt)
+          vals[cnt] = (i > 0) ? fmaf(-a.preemph, s_win[i - 1], s_win[i]) : s_win[0] * (1.0f - a.preemph);
+        __syncthreads();
+        cnt = 0;
+        for (int i = tid; i < a.full_len && cnt < 16; i += kPitchThreads, ++cnt) s_win[i] = vals[cnt];
+        __syncthreads();
+      }
+      // ---- ComputeCorrelation: subtract the mean of the first basic_len ----
+      if (warp == 0) {
+        float s = 0.0f;
+        for (int i = lane; i < a.basic_len; i += 32) s += s_win[i];
+        s = group_sum<32>(s);
+        if (lane == 0) s_scalar[0] = __fdiv_rn(s, static_cast<float>(a.basic_len));
+      }
+      __syncthreads();
+      const float mean = s_scalar[0];
+      for (int i = tid; i < a.full_len; i += kPitchThreads) s_win[i] -= mean;
+      __syncthreads();
+      if (warp == 0) {
+        float e = 0.0f;
+        for (int i = lane; i < a.basic_len; i += 32) e = fmaf(s_win[i], s_win[i], e);
+        e = group_sum<32>(e);
+        if (lane == 0) s_scalar[1] = e;
+      }
+      __syncthreads();
+      const float e1 = s_scalar[1];
+      // ---- NCCF at the integer lags: 2 threads per lag ----
+      for (int l0 = 0; l0 < nm; l0 += kPitchThreads / 2) {
+        const int l = l0 + (tid >> 1), part = tid & 1;
+        float e2 = 0.0f, inner = 0.0f;
+        if (l < nm) {
+          const int lag = a.first_lag + l;
+          const int half = (a.basic_len + 1) / 2;
+          const int i0 = part * half, i1 = min(a.basic_len, i0 + half);
+          for (int i = i0; i < i1; ++i) {
+            const float v = s_win[lag + i];
+            e2 = fmaf(v, v, e2);
+            inner = fmaf(s_win[i], v, inner);
+          }
+        }
+        e2 += __shfl_xor_sync(SNB_FULL_MASK, e2, 1);
+        inner += __shfl_xor_sync(SNB_FULL_MASK, inner, 1);
+        if (l < nm && part == 0) {
+          const float norm = __fmul_rn(e1, e2);
+          const float den_p = sqrtf(__fadd_rn(norm, ballast));
+          const float den_v = sqrtf(norm);
+          s_np[l] = den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f;
+          const float pv = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
+          s_nv[l] = pv;
+          pov_raw[f * nm + l] = pv;
+        }
+      }
+      __syncthreads();
+      // ---- upsample nccf_pitch to the log-spaced lags; local cost ----
+      float lc[kMaxStatesPerThread];
+#pragma unroll
+      for (int r = 0; r < kMaxStatesPerThread; ++r) {
+        const int i = tid + r * kPitchThreads;
+        lc[r] = 0.0f;
+        if (i < ns) {
+          const float *w = s_upw + i * a.up_nw_max;
+          const int first = s_upfirst[i], n = s_upn[i];
+          float acc = 0.0f;
+          for (int j = 0; j < n; ++j) acc = fmaf(w[j], s_np[first + j], acc);
+          // local_cost = 1 - nccf; += soft_min_f0 * lag * nccf
+          float c = __fadd_rn(1.0f, -acc);
+          c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
+          lc[r] = c;
+        }
+      }
+      // ---- exact Viterbi step: min_j pen[|i-j|] + prev[j] (first minimal j) ----
+      float lmin = FLT_MAX;
+#pragma unroll
+      for (int r = 0; r < kMaxStatesPerThread; ++r) {
+        const int i = tid + r * kPitchThreads;
+        if (i < ns) {
+          float best = FLT_MAX;
+          int bj = 0;
+          for (int j = 0; j < ns; ++j) {
+            const int d = j > i ? j - i : i - j;
+            const float c = __fadd_rn(s_pen[d], s_prev[j]);
+            if (c < best) { best = c; bj = j; }
+          }
+          bp[f * ns + i] = static_cast<int16_t>(bj);
+          const float v = __fadd_rn(best, lc[r]);
+          s_new[i] = v;
+          lmin = fminf(lmin, v);
+        }
+      }
+      // block min -> renormalise so the smallest forward cost is zero
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(SNB_FULL_MASK, lmin, o));
+      if (lane == 0) s_fred[warp] = lmin;
+      __syncthreads();
+      float gmin = s_fred[0];
+      for (int w = 1; w < kPitchThreads / 32; ++w) gmin = fminf(gmin, s_fred[w]);
+      for (int i = tid; i < ns; i += kPitchThreads) s_prev[i] = __fadd_rn(s_new[i], -gmin);
+      __syncthreads();
+    }
+    // ---- best final state (first minimum) and backtrace ----
+    {
+      float best = FLT_MAX;
+      int bi = 0x7fffffff;
+      for (int i = tid; i < ns; i += kPitchThreads)
+        if (s_prev[i] < best) { best = s_prev[i]; bi = i; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(SNB_FULL_MASK, best, o);
+        const int oi = __shfl_xor_sync(SNB_FULL_MASK, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { s_fred[warp] = best; s_ired[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        float b = s_fred[0];
+        int s = s_ired[0];
+        for (int w = 1; w < kPitchThreads / 32; ++w)
+          if (s_fred[w] < b || (s_fred[w] == b && s_ired[w] < s)) { b = s_fred[w]; s = s_ired[w]; }
+        for (int64_t f = F - 1; f >= 0; --f) {
+          states[f] = s;
+          s = bp[f * ns + s];
+        }
+      }
+      __syncthreads();
+      __threadfence_block();
+    }
+    // ---- output rows: (NCCF_pov at the chosen lag, 1 / lag) ----
+    for (int64_t f = tid; f < F; f += kPitchThreads) {
+      const int s = states[f];
+      const float *w = s_upw + s * a.up_nw_max;
+      const float *pv = pov_raw + f * nm + s_upfirst[s];
+      float acc = 0.0f;
+      for (int j = 0; j < s_upn[s]; ++j) acc = fmaf(w[j], pv[j], acc);
+      float *o = a.out + (row0 + f) * a.ld_out;
+      o[0] = acc;
+      o[1] = __fdiv_rn(1.0f, s_lags[s]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k3: ProcessPitch (OnlineProcessPitch in offline use), delay == 0
+// grid = (nutts, chunks); each CTA owns kPostRows rows of one utterance plus
+// the halo the normalisation window needs
+// ---------------------------------------------------------------------------
+constexpr int kPostRows = 128;
+
+struct PostArgs {
+  snb_pitch_post_opts o;
+  const float *raw;
+  int64_t ld_raw;
+  const int64_t *frame_offsets;
+  uint64_t seed;
+  float *out;
+  int64_t ld_out;
+  int32_t halo;        // max(left, right, delta_window)
+};
+
+__device__ __forceinline__ float nccf_to_pov(float n) {
+  float nd = fabsf(n);
+  if (nd > 1.0f) nd = 1.0f;
+  const double x = static_cast<double>(nd);
+  const float r = static_cast<float>(-5.2 + 5.4 * exp(7.5 * (x - 1.0)) + 4.8 * x - 2.0 * exp(-10.0 * x) +
+                                     4.2 * exp(20.0 * (x - 1.0)));
+  return static_cast<float>(1.0 / (1.0 + exp(-1.0 * static_cast<double>(r))));
+}
+
+__global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
+  extern __shared__ float s_post[];
+  const int64_t u = blockIdx.x;
+  const int64_t first = a.frame_offsets[u], F = a.frame_offsets[u + 1] - first;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kPostRows;
+  if (r0 >= F) return;
+  const int span = kPostRows + 2 * a.halo;
+  float *s_logp = s_post, *s_pov = s_post + span;
+  const int64_t lo = r0 - a.halo;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int64_t t = lo + i;
+    float lp = 0.0f, pv = 0.0f;
+    if (t >= 0 && t < F) {
+      const float *row = a.raw + (first + t) * a.ld_raw;
+      lp = logf(row[1]);
+      pv = nccf_to_pov(row[0]);
+    }
+    s_logp[i] = lp;
+    s_pov[i] = pv;
+  }
+  __syncthreads();
+  const snb_pitch_post_opts &o = a.o;
+  for (int r = threadIdx.x; r < kPostRows; r += blockDim.x) {
+    const int64_t t = r0 + r;
+    if (t >= F) break;
+    float *out = a.out + (first + t) * a.ld_out;
+    int col = 0;
+    const float *row = a.raw + (first + t) * a.ld_raw;
+    if (o.add_pov_feature) {
+      float n = row[0];
+      n = fminf(1.0f, fmaxf(-1.0f, n));
+      const float f = static_cast<float>(pow(1.0001 - static_cast<double>(n), 0.15) - 1.0);
+      out[col++] = __fadd_rn(__fmul_rn(o.pov_scale, f), o.pov_offset);
+    }
+    if (o.add_normalized_log_pitch) {
+      int64_t b = t - o.normalization_left_context, e = t + o.normalization_right_context + 1;
+      if (b < 0) b = 0;
+      if (e > F) e = F;
+      double sp = 0.0, slp = 0.0;
+      for (int64_t f = b; f < e; ++f) {
+        const float pv = s_pov[f - lo], lp = s_logp[f - lo];
+        sp += pv;
+        slp += static_cast<double>(__fmul_rn(pv, lp));
+      }
+      const float avg = static_cast<float>(slp / sp);
+      out[col++] = __fmul_rn(__fadd_rn(s_logp[t - lo], -avg), o.pitch_scale);
+    }
+    if (o.add_delta_pitch) {
+      const int w = o.delta_window;
+      float norm = 0.0f;
+      for (int j = -w; j <= w; ++j) norm += static_cast<float>(j * j);
+      const float inv = static_cast<float>(1.0 / static_cast<double>(norm));
+      float d = 0.0f;
+      for (int j = -w; j <= w; ++j) {
+        int64_t tt = t + j;
+        tt = tt < 0 ? 0 : (tt >= F ? F - 1 : tt);
+        const float s = __fmul_rn(static_cast<float>(j), inv);
+        if (s != 0.0f) d = fmaf(s, s_logp[tt - lo], d);
+      }
+      float noise = 0.0f;
+      if (o.delta_pitch_noise_stddev != 0.0f) {
+        float g0, g1;
+        gauss_pair(a.seed, static_cast<uint64_t>(first + t), 0u, &g0, &g1);
+        noise = g0 * o.delta_pitch_noise_stddev;
+      }
+      out[col++] = __fmul_rn(__fadd_rn(d, noise), o.delta_pitch_scale);
+    }
+    if (o.add_raw_log_pitch) out[col++] = s_logp[t - lo];
+  }
+}
+
+static int pitch_grid(int64_t nutts) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  return static_cast<int>(std::min<int64_t>(nutts, static_cast<int64_t>(sms) * 4));
+}
+
+static size_t track_smem(const PitchTables *t) {
+  return static_cast<size_t>(t->full_len + 2 * t->nmeas + 4 * t->nstates + t->nstates * t->up_nw_max) * 4 +
+         static_cast<size_t>(2 * t->nstates) * 4 + 16;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int64_t snb_pitch_num_frames(int64_t nsamples, const snb_pitch_opts *po) {
+  if (!pitch_opts_valid(*po)) return 0;
+  int32_t first, last;
+  lag_range(*po, &first, &last);
+  return frames_available(resample_num_out(nsamples, *po, true), *po, last, true);
+}
+
+extern "C" int snb_pitch_plan_create(const snb_pitch_opts *po, snb_plan **out) {
+  if (!po || !out) return set_error(SNB_ERR_VALUE, "null argument");
+  *out = nullptr;
+  snb_plan *plan = new snb_plan();
+  plan->kind = 1;
+  plan->po = *po;
+  cudaGetDevice(&plan->device);
+  cudaGetLastError();
+  int rc = pitch_plan_init(plan);
+  if (rc != SNB_OK) {
+    pitch_plan_free(plan);
+    delete plan;
+    return rc;
+  }
+  *out = plan;
+  return SNB_OK;
+}
+
+static int64_t max_frames_of(const snb_batch *b) {
+  int64_t m = 0;
+  for (int64_t u = 0; u < b->nutts; ++u) m = std::max(m, b->frame_offsets[u + 1] - b->frame_offsets[u]);
+  return m;
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
+  if (!plan || plan->kind != 1 || !batch) return -1;
+  const PitchTables *t = plan->pitch;
+  const int64_t grid = pitch_grid(batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
+  size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4);
+  bytes += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
+  bytes += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
+  bytes += align256(static_cast<size_t>(grid) * mf * 4);
+  return static_cast<int64_t>(bytes);
+}
+
+extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
+                                 void *d_workspace, int64_t workspace_bytes, float *d_out, int64_t ld_out,
+                                 void *stream_) {
+  if (!plan || plan->kind != 1 || !batch || batch->plan != plan)
+    return set_error(SNB_ERR_VALUE, "plan/batch mismatch");
+  if (batch->total_frames == 0) return SNB_OK;
+  if (!d_pcm || !d_out || !d_workspace || ld_out < 2) return set_error(SNB_ERR_VALUE, "bad argument");
+  if (workspace_bytes < snb_pitch_workspace_bytes(plan, batch))
+    return set_error(SNB_ERR_VALUE, "pitch workspace too small");
+  const PitchTables *t = plan->pitch;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t grid = pitch_grid(batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
+  unsigned char *ws = static_cast<unsigned char *>(d_workspace);
+  float *down = reinterpret_cast<float *>(ws);
+  ws += align256(static_cast<size_t>(batch->total_down + 8) * 4);
+  int16_t *bp = reinterpret_cast<int16_t *>(ws);
+  ws += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
+  float *pov_raw = reinterpret_cast<float *>(ws);
+  ws += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
+  int32_t *states = reinterpret_cast<int32_t *>(ws);
+
+  ResampleArgs r;
+  r.pcm = d_pcm;
+  r.sample_begin = batch->d_sample_begin;
+  r.sample_len = batch->d_sample_len;
+  r.info = batch->d_down_offsets;
+  r.nutts = batch->nutts;
+  r.total_down = batch->total_down;
+  r.in_unit = t->in_unit; r.out_unit = t->out_unit; r.nw_max = t->down_nw_max;
+  r.first = t->d_down_first; r.nw = t->d_down_nw; r.w = t->d_down_w;
+  r.down = down;
+  if (batch->total_down > 0) {
+    resample_kernel<<<static_cast<unsigned>((batch->total_down + 255) / 256), 256, 0, stream>>>(r);
+    SNB_LAUNCH_CHECK();
+  }
+  TrackArgs a;
+  a.down = down;
+  a.info = batch->d_down_offsets;
+  a.frame_offsets = batch->d_frame_offsets;
+  a.nutts = batch->nutts;
+  a.first_lag = t->first_lag; a.nmeas = t->nmeas; a.nstates = t->nstates;
+  a.shift = t->shift; a.basic_len = t->basic_len; a.full_len = t->full_len; a.up_nw_max = t->up_nw_max;
+  a.snip_edges = plan->po.snip_edges;
+  a.preemph = plan->po.preemph_coeff;
+  a.soft_min_f0 = plan->po.soft_min_f0;
+  a.nccf_ballast = plan->po.nccf_ballast;
+  a.lags = t->d_lags; a.pen = t->d_pen; a.up_w = t->d_up_w;
+  a.up_first = t->d_up_first; a.up_nw = t->d_up_nw;
+  a.bp = bp; a.pov_raw = pov_raw; a.states = states;
+  a.max_frames = mf;
+  a.out = d_out; a.ld_out = ld_out;
+  const size_t smem = track_smem(t);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
+  }
+  pitch_track_kernel<<<static_cast<unsigned>(grid), kPitchThreads, smem, stream>>>(a);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int32_t snb_process_pitch_dim(const snb_pitch_post_opts *o) {
+  return (o->add_pov_feature != 0) + (o->add_normalized_log_pitch != 0) + (o->add_delta_pitch != 0) +
+         (o->add_raw_log_pitch != 0);
+}
+
+extern "C" int snb_process_pitch(const snb_pitch_post_opts *o, const float *d_raw, int64_t ld_raw,
+                                 const int64_t *d_frame_offsets, int64_t nutts, int64_t total_frames,
+                                 int64_t max_frames, uint64_t seed, float *d_out, int64_t ld_out,
+                                 void *stream) {
+  if (!o) return set_error(SNB_ERR_VALUE, "null options");
+  const int dim = snb_process_pitch_dim(o);
+  if (dim == 0)
+    return set_error(SNB_ERR_VALUE, "at least one of the pitch features must be enabled");
+  if (o->delay != 0) return set_error(SNB_ERR_UNSUPPORTED, "delay != 0 is not supported on the GPU path");
+  if (total_frames == 0 || nutts == 0) return SNB_OK;
+  if (!d_raw || !d_out || ld_raw < 2 || ld_out < dim) return set_error(SNB_ERR_VALUE, "bad argument");
+  if (o->normalization_left_context < 0 || o->normalization_right_context < 0 || o->delta_window <= 0)
+    return set_error(SNB_ERR_VALUE, "invalid pitch post-processing contexts");
+  PostArgs a;
+  a.o = *o;
+  a.raw = d_raw; a.ld_raw = ld_raw;
+  a.frame_offsets = d_frame_offsets;
+  a.seed = seed;
+  a.out = d_out; a.ld_out = ld_out;
+  a.halo = std::max(std::max(o->normalization_left_context, o->normalization_right_context), o->delta_window);
+  const size_t smem = static_cast<size_t>(kPostRows + 2 * a.halo) * 2 * 4;
+  if (smem > 200 * 1024) return set_error(SNB_ERR_UNSUPPORTED, "normalisation context too large");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(process_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "post smem: %s", cudaGetErrorString(e));
+  }
+  const unsigned chunks = static_cast<unsigned>((std::max<int64_t>(max_frames, 1) + kPostRows - 1) / kPostRows);
+  if (chunks > 65535) return set_error(SNB_ERR_UNSUPPORTED, "utterance too long for process_pitch");
+  process_pitch_kernel<<<dim3(static_cast<unsigned>(nutts), chunks), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

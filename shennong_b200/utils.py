@@ -1,0 +1,51 @@
+"""Small host utilities (counterpart of shennong/utils.py)"""
+
+import multiprocessing
+
+import numpy as np
+
+from shennong_b200.logger import null_logger
+
+
+def get_njobs(njobs=None, log=null_logger()):
+    """Number of parallel jobs, clipped to the number of CPU cores
+
+    On the GPU engine `njobs` only sizes the host-side audio loading pool:
+    the extraction itself is one batched launch.  Raises ValueError when
+    `njobs` is not strictly positive (shennong/utils.py:16-47).
+    """
+    ncores = multiprocessing.cpu_count()
+    if njobs is None:
+        return ncores
+    if njobs <= 0:
+        raise ValueError(
+            'njobs must be strictly positive, it is {}'.format(njobs))
+    if njobs > ncores:
+        log.warning(
+            'asking %d CPU cores but reducing to %d (max available)',
+            njobs, ncores)
+        return ncores
+    return njobs
+
+
+def array2list(obj):
+    """Recursively converts numpy arrays of `obj` to lists"""
+    if isinstance(obj, dict):
+        return {k: array2list(v) for k, v in obj.items()}
+    if isinstance(obj, np.ndarray):
+        return obj.tolist()
+    return obj
+
+
+def list2array(obj):
+    """Recursively converts lists of `obj` to numpy arrays"""
+    if isinstance(obj, list):
+        return np.asarray(obj)
+    if isinstance(obj, dict):
+        return {k: list2array(v) for k, v in obj.items()}
+    return obj
+
+
+def dict_equal(dict1, dict2):
+    """Equality of dicts that may hold numpy arrays (shennong/utils.py:78-96)"""
+    return array2list(dict1) == array2list(dict2)
