@@ -112,8 +112,21 @@ static float extract_window(const float *wave, int64_t nsamples, int32_t frame,
     }
   }
   for (int32_t s = len; s < padded; s++) window[s] = 0.0f;
-  /* dither is stochastic in the reference (libc rand): parity is only
-   * defined for dither == 0, the oracle ignores it. */
+  /* dither is stochastic in the reference (RandGauss on libc rand()): parity
+   * is only defined for dither == 0.  For the CPU-baseline timing the oracle
+   * draws Box-Muller normals with the same arithmetic cost as Kaldi's
+   * RandGauss (one log, sqrt and cos per sample) from a counter-based hash. */
+  if (o->dither != 0.0f) {
+    for (int32_t s = 0; s < len; s++) {
+      uint64_t z = ((uint64_t)frame * 8192u + (uint64_t)s + 1u) * 0x9e3779b97f4a7c15ull;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      z ^= z >> 31;
+      float u1 = ((float)((uint32_t)z >> 8) + 1.0f) * (1.0f / 16777216.0f);
+      float u2 = (float)((uint32_t)(z >> 40)) * (1.0f / 16777216.0f);
+      window[s] += o->dither * (sqrtf(-2.0f * logf(u1)) * cosf(6.2831853f * u2));
+    }
+  }
   if (o->remove_dc_offset) {
     double sum = 0.0; /* VectorBase<float>::Sum() accumulates in double */
     for (int32_t s = 0; s < len; s++) sum += window[s];
@@ -142,53 +155,84 @@ static float extract_window(const float *wave, int64_t nsamples, int32_t frame,
  * FFT evaluated in double; re/im rounded to float; power formed in float like
  * ComputePowerSpectrum does.                                                */
 
-static void fft_pow2(double *re, double *im, int32_t n) {
-  for (int32_t i = 1, j = 0; i < n; i++) {
-    int32_t bit = n >> 1;
-    for (; j & bit; bit >>= 1) j ^= bit;
-    j ^= bit;
-    if (i < j) {
-      double t = re[i]; re[i] = re[j]; re[j] = t;
-      t = im[i]; im[i] = im[j]; im[j] = t;
-    }
+/* twiddle/bit-reversal tables of a plan (double precision) */
+typedef struct {
+  int32_t n;          /* real FFT size */
+  int32_t pow2;
+  double *wr, *wi;    /* e^{-2 pi i k / n}, k < n   */
+  int32_t *rev;       /* bit reversal for the n/2-point complex FFT */
+} orc_fft;
+
+static void fft_init(orc_fft *f, int32_t n) {
+  f->n = n;
+  f->pow2 = (n & (n - 1)) == 0 && n >= 4;
+  f->wr = (double *)malloc(sizeof(double) * n);
+  f->wi = (double *)malloc(sizeof(double) * n);
+  for (int32_t k = 0; k < n; k++) {
+    f->wr[k] = cos(-M_2PI * k / n);
+    f->wi[k] = sin(-M_2PI * k / n);
   }
-  for (int32_t len = 2; len <= n; len <<= 1) {
-    double ang = -M_2PI / len;
-    for (int32_t i = 0; i < n; i += len) {
-      for (int32_t k = 0; k < len / 2; k++) {
-        double wr = cos(ang * k), wi = sin(ang * k);
-        double ur = re[i + k], ui = im[i + k];
-        double vr = re[i + k + len / 2] * wr - im[i + k + len / 2] * wi;
-        double vi = re[i + k + len / 2] * wi + im[i + k + len / 2] * wr;
-        re[i + k] = ur + vr; im[i + k] = ui + vi;
-        re[i + k + len / 2] = ur - vr; im[i + k + len / 2] = ui - vi;
-      }
+  f->rev = NULL;
+  if (f->pow2) {
+    int32_t m = n / 2;
+    f->rev = (int32_t *)malloc(sizeof(int32_t) * m);
+    for (int32_t i = 0, j = 0; i < m; i++) {
+      f->rev[i] = j;
+      int32_t bit = m >> 1;
+      for (; bit && (j & bit); bit >>= 1) j ^= bit;
+      j ^= bit;
     }
   }
 }
+static void fft_free(orc_fft *f) { free(f->wr); free(f->wi); free(f->rev); }
 
-/* frame: [n] in, power: [n/2+1] out */
-static void power_spectrum(const float *frame, int32_t n, float *power,
-                           double *wr, double *wi) {
-  int32_t half = n / 2;
-  if ((n & (n - 1)) == 0) {
-    for (int32_t i = 0; i < n; i++) { wr[i] = frame[i]; wi[i] = 0.0; }
-    fft_pow2(wr, wi, n);
+/* frame: [n] in, power: [n/2+1] out; zr/zi: scratch [n] */
+static void power_spectrum(const orc_fft *f, const float *frame, float *power,
+                           double *zr, double *zi) {
+  const int32_t n = f->n, half = n / 2;
+  double *xr = zr + half, *xi = zi + half; /* second halves hold X */
+  if (f->pow2) {
+    /* packed real FFT: z[j] = x[2j] + i x[2j+1], m-point complex FFT */
+    const int32_t m = half;
+    for (int32_t j = 0; j < m; j++) {
+      zr[f->rev[j]] = frame[2 * j];
+      zi[f->rev[j]] = frame[2 * j + 1];
+    }
+    for (int32_t len = 2; len <= m; len <<= 1) {
+      const int32_t h = len >> 1, step = n / len; /* e^{-2 pi i k/len} = w[k*step] */
+      for (int32_t i = 0; i < m; i += len)
+        for (int32_t k = 0; k < h; k++) {
+          const double wr = f->wr[k * step], wi = f->wi[k * step];
+          const double vr = zr[i + k + h] * wr - zi[i + k + h] * wi;
+          const double vi = zr[i + k + h] * wi + zi[i + k + h] * wr;
+          const double ur = zr[i + k], ui = zi[i + k];
+          zr[i + k] = ur + vr; zi[i + k] = ui + vi;
+          zr[i + k + h] = ur - vr; zi[i + k + h] = ui - vi;
+        }
+    }
+    for (int32_t k = 0; k <= m; k++) {
+      const int32_t a = k % m, b = (m - k) % m;
+      const double er = 0.5 * (zr[a] + zr[b]), ei = 0.5 * (zi[a] - zi[b]);
+      const double orr = 0.5 * (zi[a] + zi[b]), oi = -0.5 * (zr[a] - zr[b]);
+      const double wr = (k == m) ? -1.0 : f->wr[k], wi = (k == m) ? 0.0 : f->wi[k];
+      xr[k] = er + orr * wr - oi * wi;
+      xi[k] = ei + orr * wi + oi * wr;
+    }
   } else {
     for (int32_t k = 0; k <= half; k++) {
       double sr = 0.0, si = 0.0;
+      int32_t idx = 0;
       for (int32_t t = 0; t < n; t++) {
-        int64_t idx = ((int64_t)k * t) % n;
-        double ang = -M_2PI * (double)idx / n;
-        sr += frame[t] * cos(ang);
-        si += frame[t] * sin(ang);
+        sr += frame[t] * f->wr[idx];
+        si += frame[t] * f->wi[idx];
+        idx += k; if (idx >= n) idx -= n;
       }
-      wr[k] = sr; wi[k] = si;
+      xr[k] = sr; xi[k] = si;
     }
   }
   for (int32_t k = 0; k <= half; k++) {
-    float r = (float)wr[k], i = (float)wi[k];
-    if (k == 0 || k == half) power[k] = r * r; /* purely real bins */
+    float r = (float)xr[k], i = (float)xi[k];
+    if (k == 0 || 2 * k == n) power[k] = r * r; /* purely real bins */
     else power[k] = r * r + i * i;
   }
 }
@@ -296,12 +340,14 @@ typedef struct {
   float *idft;       /* [lpc_order+1, num_bins+2] */
   float log_energy_floor;
   double eps;
+  orc_fft fft;
 } orc_plan;
 
 static void plan_free(orc_plan *p) {
   free(p->window_fn); free(p->mel_w); free(p->mel_first); free(p->mel_size);
   free(p->center_freqs); free(p->dct); free(p->lifter); free(p->loudness);
   free(p->idft);
+  if (p->fft.wr) fft_free(&p->fft);
   memset(p, 0, sizeof(*p));
 }
 
@@ -339,6 +385,7 @@ static int32_t plan_init(orc_plan *p, const orc_frame_opts *fo,
   p->dim = orc_feat_dim(&p->fo, &p->mo, xo);
   if (p->dim <= 0) return -1;
   p->eps = (xo->kind == ORC_FEAT_PLP) ? DBL_EPSILON : (double)FLT_EPSILON;
+  if (xo->kind != ORC_FEAT_ENERGY) fft_init(&p->fft, p->padded);
   p->window_fn = (float *)malloc(sizeof(float) * p->len);
   orc_window_function(&p->fo, p->window_fn);
   if (xo->energy_floor > 0.0f)
@@ -530,7 +577,7 @@ static void compute_frame(const orc_plan *p, float raw_log_energy,
     default: post_window_energy = xo->use_energy && !xo->raw_energy;
   }
   if (post_window_energy) log_energy = log_energy_of(frame, p->padded, p->eps);
-  power_spectrum(frame, p->padded, power, wr, wi);
+  power_spectrum(&p->fft, frame, power, wr, wi);
   int32_t nb = p->mo.num_bins;
   if (xo->kind == ORC_FEAT_SPECTROGRAM) {
     for (int32_t k = 0; k <= p->nfft_bins; k++) {
@@ -629,8 +676,8 @@ static int64_t compute_with_plan(const orc_plan *p, const float *wave,
   if (nframes <= 0) return nframes < 0 ? -1 : 0;
   const orc_feat_opts *xo = &p->xo;
   float *frame = (float *)malloc(sizeof(float) * p->padded);
-  double *wr = (double *)malloc(sizeof(double) * p->padded);
-  double *wi = (double *)malloc(sizeof(double) * p->padded);
+  double *wr = (double *)malloc(sizeof(double) * (p->padded + 2));
+  double *wi = (double *)malloc(sizeof(double) * (p->padded + 2));
   float *power = (float *)malloc(sizeof(float) * (p->nfft_bins + 1));
   float *mel = (float *)malloc(sizeof(float) * (p->mo.num_bins + 2 + 1));
   rasta_state rasta; int have_rasta = 0;
@@ -771,7 +818,7 @@ int32_t orc_cmvn_apply(const double *stats, int32_t dim, int32_t norm_vars,
   const double *s0 = stats, *s1 = stats + (dim + 1);
   if (!reverse && !norm_vars) {
     for (int32_t d = 0; d < dim; d++) {
-      float offset = (float)(-1.0 / count * s0[d]);
+      float offset = (float)((double)(float)(-1.0 / count) * s0[d]);
       for (int64_t t = 0; t < nframes; t++) feats[(size_t)t * dim + d] += offset;
     }
     return 0;

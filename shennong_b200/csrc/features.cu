@@ -675,13 +675,6 @@ int feature_plan_finalize(snb_plan *plan) {
     if (sm.total <= 200 * 1024) {
       plan->fast_path = true;
       plan->smem_bytes = sm.total;
-      cudaError_t e = cudaFuncSetAttribute(fused_features_512_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total);
-      if (e != cudaSuccess) {
-        // no usable device (e.g. symbol-export tests on a CPU box): keep the
-        // plan, the error will surface at the first compute call
-        cudaGetLastError();
-      }
       return SNB_OK;
     }
   }
@@ -696,10 +689,6 @@ int feature_plan_finalize(snb_plan *plan) {
   plan->smem_bytes = static_cast<size_t>(align_up(tables, 4) + kGenWarps * align_up(warp_floats, 4)) * 4;
   if (plan->smem_bytes > 220 * 1024)
     return set_error(SNB_ERR_UNSUPPORTED, "options need too much shared memory");
-  cudaError_t e = cudaFuncSetAttribute(generic_features_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(plan->smem_bytes));
-  if (e != cudaSuccess) cudaGetLastError();
   return SNB_OK;
 }
 
@@ -1016,6 +1005,22 @@ extern "C" const int64_t *snb_batch_frame_offsets_device(const snb_batch *b) { r
 // ---------------------------------------------------------------------------
 // host: launch
 // ---------------------------------------------------------------------------
+// the max-dynamic-smem attribute is per function: only ever raise it
+template <typename K>
+static int ensure_smem(K kernel, size_t bytes, std::atomic<size_t> *current) {
+  size_t cur = current->load();
+  while (bytes > cur) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(bytes));
+    if (e != cudaSuccess)
+      return set_error(SNB_ERR_CUDA, "cannot reserve %zu bytes of shared memory: %s", bytes,
+                       cudaGetErrorString(e));
+    if (current->compare_exchange_weak(cur, bytes)) break;
+  }
+  return SNB_OK;
+}
+static std::atomic<size_t> g_fast_smem{0}, g_gen_smem{0};
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -1057,6 +1062,8 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
     a.seed = seed;
     static const bool no_tma = getenv("SNB_NO_TMA") != nullptr;
     a.use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(d_pcm) % 16 == 0)) ? 1 : 0;
+    int rc = ensure_smem(fused_features_512_kernel, a.sm.total, &g_fast_smem);
+    if (rc != SNB_OK) return rc;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_features_512_kernel, kFastThreads,
                                                   a.sm.total);
@@ -1092,13 +1099,11 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
   g.out = d_out;
   g.ld_out = ld_out;
   g.seed = seed;
-  size_t smem = plan->smem_bytes;
-  if (plan->fast_path) {
-    // float input on a plan whose batches are tiled for the fast path (energy)
-    smem = static_cast<size_t>(g.tables_floats + kGenWarps * g.warp_floats) * 4;
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(generic_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(smem));
+  // (also reached with float input on a plan tiled for the fast path: energy)
+  const size_t smem = static_cast<size_t>(g.tables_floats + kGenWarps * g.warp_floats) * 4;
+  {
+    int rc = ensure_smem(generic_features_kernel, smem, &g_gen_smem);
+    if (rc != SNB_OK) return rc;
   }
   const int64_t want = (batch->total_frames + kGenWarps - 1) / kGenWarps;
   const int64_t grid = std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 8);

@@ -744,10 +744,15 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   a.max_frames = mf;
   a.out = d_out; a.ld_out = ld_out;
   const size_t smem = track_smem(t);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
+  {
+    static std::atomic<size_t> cur{48 * 1024};
+    size_t c = cur.load();
+    while (smem > c) {
+      cudaError_t e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
+      if (cur.compare_exchange_weak(c, smem)) break;
+    }
   }
   pitch_track_kernel<<<static_cast<unsigned>(grid), kPitchThreads, smem, stream>>>(a);
   SNB_LAUNCH_CHECK();
@@ -781,10 +786,15 @@ extern "C" int snb_process_pitch(const snb_pitch_post_opts *o, const float *d_ra
   a.halo = std::max(std::max(o->normalization_left_context, o->normalization_right_context), o->delta_window);
   const size_t smem = static_cast<size_t>(kPostRows + 2 * a.halo) * 2 * 4;
   if (smem > 200 * 1024) return set_error(SNB_ERR_UNSUPPORTED, "normalisation context too large");
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(process_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "post smem: %s", cudaGetErrorString(e));
+  {
+    static std::atomic<size_t> cur{48 * 1024};
+    size_t c = cur.load();
+    while (smem > c) {
+      cudaError_t e = cudaFuncSetAttribute(process_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "post smem: %s", cudaGetErrorString(e));
+      if (cur.compare_exchange_weak(c, smem)) break;
+    }
   }
   const unsigned chunks = static_cast<unsigned>((std::max<int64_t>(max_frames, 1) + kPostRows - 1) / kPostRows);
   if (chunks > 65535) return set_error(SNB_ERR_UNSUPPORTED, "utterance too long for process_pitch");

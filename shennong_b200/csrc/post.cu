@@ -187,7 +187,8 @@ __global__ void cmvn_norm_kernel(const double *stats, int64_t ngroups, int dim, 
     if (!norm_vars) {
       scale = 1.0f;
       // ApplyCmvn: offset.AddVec(-1.0 / count, mean_stats)
-      offset = reverse ? static_cast<float>(mean) : static_cast<float>(-1.0 / count * s[d]);
+      offset = reverse ? static_cast<float>(mean)
+                       : static_cast<float>(static_cast<double>(static_cast<float>(-1.0 / count)) * s[d]);
     } else {
       double var = s[(dim + 1) + d] / count - mean * mean;
       if (var < 1.0e-20) var = 1.0e-20;
