@@ -2,24 +2,10 @@
 
     Features --> FeaturesPostProcessor --> Features
 
-(counterpart of shennong/postprocessor/base.py)
+(counterpart of shennong/postprocessor/base.py; the class body lives in
+shennong_b200.processor.base to keep the two packages free of import cycles)
 """
 
-import abc
-import copy
+from shennong_b200.processor.base import FeaturesPostProcessor
 
-from shennong_b200.processor.base import FeaturesProcessor
-
-
-class FeaturesPostProcessor(FeaturesProcessor):
-    """Base class of all features post-processors"""
-    @abc.abstractmethod
-    def process(self, features):
-        """Returns features post-processed from input `features`"""
-
-    def get_properties(self, features):
-        properties = copy.deepcopy(features.properties)
-        properties[self.name] = self.get_params()
-        properties.setdefault('pipeline', []).append(
-            {'name': self.name, 'columns': [0, self.ndims - 1]})
-        return properties
+__all__ = ['FeaturesPostProcessor']

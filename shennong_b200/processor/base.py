@@ -11,6 +11,7 @@ a CPU thread per utterance.
 
 import abc
 import concurrent.futures
+import copy
 
 import numpy as np
 
@@ -80,6 +81,26 @@ class FeaturesProcessor(BaseProcessor, metaclass=abc.ABCMeta):
         feats = self._process_batch(
             audios, **{k: [v[n] for n in names] for k, v in kwargs.items()})
         return FeaturesCollection(zip(names, feats))
+
+
+class FeaturesPostProcessor(FeaturesProcessor):
+    """Base class of all features post-processors (Features -> Features)
+
+    Defined here (and re-exported by shennong_b200.postprocessor.base, where
+    the reference has it: shennong/postprocessor/base.py:15-32) so that the
+    pitch post-processor, which lives in the processor package like in the
+    reference, does not create an import cycle.
+    """
+    @abc.abstractmethod
+    def process(self, features):
+        """Returns features post-processed from input `features`"""
+
+    def get_properties(self, features):
+        properties = copy.deepcopy(features.properties)
+        properties[self.name] = self.get_params()
+        properties.setdefault('pipeline', []).append(
+            {'name': self.name, 'columns': [0, self.ndims - 1]})
+        return properties
 
 
 def _check_window(_, value):

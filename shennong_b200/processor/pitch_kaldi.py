@@ -14,8 +14,8 @@ import numpy as np
 from shennong_b200 import _lib, engine
 from shennong_b200.base import Option, f32_py, ms_load, ms_store
 from shennong_b200.features import Features
-from shennong_b200.postprocessor.base import FeaturesPostProcessor
-from shennong_b200.processor.base import FeaturesProcessor
+from shennong_b200.processor.base import (
+    FeaturesPostProcessor, FeaturesProcessor)
 
 
 class KaldiPitchProcessor(FeaturesProcessor):

@@ -182,7 +182,11 @@ def test_edge_lengths():
     zeros = np.zeros(3000, np.int16)
     for kind in ('mfcc', 'filterbank', 'spectrogram'):
         feats = run(kind, zeros)
-        assert np.array_equal(feats.data, oracle.features(kind, zeros))
+        # (the DCT of a constant vector is rounding noise around 0)
+        assert np.allclose(feats.data, oracle.features(kind, zeros),
+                           rtol=0, atol=1e-4)
+        if kind != 'mfcc':
+            assert np.array_equal(feats.data, oracle.features(kind, zeros))
     # full-scale square wave (maximum magnitudes)
     square = (np.sign(np.sin(np.arange(8000) * 0.05)) * 32767).astype(np.int16)
     scale_close(run('mfcc', square).data, oracle.features('mfcc', square))
