@@ -835,7 +835,7 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
   float *d = nullptr;
   cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float));
   if (e == cudaSuccess)
-    e = cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    e = upload(d, host.data(), host.size() * sizeof(float));
   if (e != cudaSuccess) {
     // Without a usable GPU the product cannot run: fail loudly.
     cudaGetLastError();
@@ -904,12 +904,11 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
   if (e == cudaSuccess) e = cudaMalloc(&b->d_sample_len, (nutts + 1) * sizeof(int64_t));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_frame_offsets, (nutts + 1) * sizeof(int64_t));
   if (e == cudaSuccess && nutts > 0)
-    e = cudaMemcpy(b->d_sample_begin, b->sample_begin.data(), nutts * sizeof(int64_t), cudaMemcpyHostToDevice);
+    e = upload(b->d_sample_begin, b->sample_begin.data(), nutts * sizeof(int64_t));
   if (e == cudaSuccess && nutts > 0)
-    e = cudaMemcpy(b->d_sample_len, b->sample_len.data(), nutts * sizeof(int64_t), cudaMemcpyHostToDevice);
+    e = upload(b->d_sample_len, b->sample_len.data(), nutts * sizeof(int64_t));
   if (e == cudaSuccess)
-    e = cudaMemcpy(b->d_frame_offsets, b->frame_offsets.data(), (nutts + 1) * sizeof(int64_t),
-                   cudaMemcpyHostToDevice);
+    e = upload(b->d_frame_offsets, b->frame_offsets.data(), (nutts + 1) * sizeof(int64_t));
   if (e != cudaSuccess)
     return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
   if (plan->kind == 1) {
@@ -946,7 +945,7 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
     }
     e = cudaMalloc(&b->d_mel_blobs, blobs.size() * sizeof(int32_t));
     if (e == cudaSuccess)
-      e = cudaMemcpy(b->d_mel_blobs, blobs.data(), blobs.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+      e = upload(b->d_mel_blobs, blobs.data(), blobs.size() * sizeof(int32_t));
     if (e != cudaSuccess)
       return fail(set_error(SNB_ERR_CUDA, "mel upload failed: %s", cudaGetErrorString(e)));
   }
@@ -969,7 +968,7 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
     if (b->ntiles > 0) {
       e = cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc));
       if (e == cudaSuccess)
-        e = cudaMemcpy(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice);
+        e = upload(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc));
       if (e != cudaSuccess)
         return fail(set_error(SNB_ERR_CUDA, "tile upload failed: %s", cudaGetErrorString(e)));
     }
@@ -978,7 +977,7 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
     if (nutts > 0) {
       e = cudaMalloc(&b->d_tiles, nutts * sizeof(int32_t));
       if (e == cudaSuccess)
-        e = cudaMemcpy(b->d_tiles, utt_mel.data(), nutts * sizeof(int32_t), cudaMemcpyHostToDevice);
+        e = upload(b->d_tiles, utt_mel.data(), nutts * sizeof(int32_t));
       if (e != cudaSuccess)
         return fail(set_error(SNB_ERR_CUDA, "index upload failed: %s", cudaGetErrorString(e)));
     }

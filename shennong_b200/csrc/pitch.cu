@@ -200,7 +200,7 @@ int pitch_plan_init(snb_plan *plan) {
                o8 = push_f(t->up_w);
   int32_t *d = nullptr;
   cudaError_t e = cudaMalloc(&d, blob.size() * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(d, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = upload(d, blob.data(), blob.size() * 4);
   if (e != cudaSuccess) {
     cudaGetLastError();
     if (d) cudaFree(d);
@@ -243,7 +243,7 @@ int pitch_batch_init(const snb_plan *plan, snb_batch *b) {
   b->down_offsets = info;
   cudaError_t e = cudaMalloc(&b->d_down_offsets, info.size() * sizeof(int64_t));
   if (e == cudaSuccess)
-    e = cudaMemcpy(b->d_down_offsets, info.data(), info.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
+    e = upload(b->d_down_offsets, info.data(), info.size() * sizeof(int64_t));
   if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch batch upload failed: %s", cudaGetErrorString(e));
   return SNB_OK;
 }

@@ -346,7 +346,9 @@ extern "C" int snb_cmvn_accumulate(const float *d_feats, int64_t ld, int32_t dim
                                    const int64_t *d_frame_offsets, int64_t nutts, const float *d_weights,
                                    double *d_utt_stats, void *stream) {
   if (nutts == 0) return SNB_OK;
-  if (!d_feats || !d_utt_stats || !d_frame_offsets || dim <= 0 || ld < dim)
+  // d_feats may be NULL when the batch holds no frame at all (the kernel then
+  // only writes zero statistics)
+  if (!d_utt_stats || !d_frame_offsets || dim <= 0 || ld < dim)
     return set_error(SNB_ERR_VALUE, "bad argument");
   cmvn_accumulate_kernel<<<static_cast<unsigned>(nutts), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       d_feats, ld, dim, d_frame_offsets, d_weights, d_utt_stats);

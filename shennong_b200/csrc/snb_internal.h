@@ -36,6 +36,12 @@ extern std::atomic<int64_t> g_launch_count;
                             cudaGetErrorString(err__), __FILE__, __LINE__);  \
   } while (0)
 
+// Host -> device upload that is COMPLETE on return for every stream: a plain
+// cudaMemcpy from pageable memory may return once the data is staged, with the
+// DMA only ordered in the legacy stream -- kernels launched on non-blocking
+// streams (PyTorch's) could then read the destination too early.
+cudaError_t upload(void *dst, const void *src, size_t bytes);
+
 // ---- host-side tables (tables.cc) ------------------------------------------
 int32_t window_size(const snb_frame_opts &o);
 int32_t window_shift(const snb_frame_opts &o);

@@ -25,6 +25,23 @@ int set_error(int code, const char *fmt, ...) {
 }
 const char *last_error() { return g_error; }
 
+cudaError_t upload(void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  static thread_local cudaStream_t stream = nullptr;
+  static thread_local int stream_device = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (stream == nullptr || stream_device != dev) {
+    e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    stream_device = dev;
+  }
+  e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(stream);
+}
+
 int32_t window_shift(const snb_frame_opts &o) {
   return static_cast<int32_t>(static_cast<double>(o.samp_freq) * 0.001 *
                               static_cast<double>(o.frame_shift_ms));
