@@ -1,0 +1,432 @@
+"""Speech features extraction pipeline (counterpart of shennong/pipeline.py)
+
+    features (+ VTLN warps) -> CMVN (by speaker or utterance, optional VAD)
+    -> delta   ‖   pitch -> pitch post-processing      => column concatenation
+
+Same configuration surface (dict / YAML, :func:`get_default_config`) and same
+entry point :func:`extract_features`, but the schedule is batched: the
+utterances are loaded on host threads (`njobs`), packed, and the whole
+two-pass schedule of the reference (pipeline.py:541-567) runs as a short
+sequence of fused launches on the device
+(:class:`shennong_b200.fused.FusedPipeline`).
+
+>>> from shennong_b200 import pipeline
+>>> config = pipeline.get_default_config('mfcc', with_cmvn=True)
+>>> sorted(config.keys())
+['cmvn', 'mfcc']
+"""
+
+import concurrent.futures
+import copy
+import os
+import textwrap
+
+import numpy as np
+import yaml
+
+from shennong_b200 import engine
+from shennong_b200.features import Features
+from shennong_b200.features_collection import FeaturesCollection
+from shennong_b200.fused import FusedPipeline
+from shennong_b200.logger import get_logger
+from shennong_b200.pipeline_manager import PipelineManager
+from shennong_b200.utils import get_njobs
+
+
+def valid_features():
+    """The main features available to the pipeline"""
+    return PipelineManager.valid_features
+
+
+def get_default_config(features, to_yaml=False, yaml_commented=True,
+                       with_pitch=False, with_cmvn=False, with_delta=False,
+                       with_vtln=False):
+    """Default configuration of the pipeline for `features`
+
+    Returns a dict, or a YAML string if `to_yaml` (with the parameters
+    docstrings as comments if `yaml_commented`).  `with_pitch` is False or
+    'kaldi'.  Raises ValueError on invalid arguments; 'crepe' pitch and VTLN
+    estimation are not provided by this engine.
+    """
+    if features not in valid_features():
+        raise ValueError('invalid features "{}", must be in {}'.format(
+            features, ', '.join(valid_features())))
+    if with_pitch not in (False, 'kaldi', 'crepe'):
+        raise ValueError(
+            f'with_pitch argument must be False, "kaldi" or "crepe" '
+            f'but is "{with_pitch}"')
+    if with_pitch == 'crepe':
+        PipelineManager.get_processor_class('crepe_pitch')   # raises
+    if with_vtln not in (False, 'simple', 'full'):
+        raise ValueError(
+            f'with_vtln argument must be False, "simple" or "full" '
+            f'but is "{with_vtln}"')
+    if with_vtln:
+        PipelineManager.get_processor_class('vtln')          # raises
+
+    params = PipelineManager.get_processor_params
+    config = {features: {
+        k: v for k, v in params(features).items()
+        if k not in ('sample_rate', 'htk_compat')}}
+    if with_pitch:
+        config['pitch'] = {'processor': with_pitch}
+        config['pitch'].update(
+            (k, v) for k, v in params('kaldi_pitch').items()
+            if k not in ('frame_length', 'frame_shift', 'sample_rate'))
+        config['pitch']['postprocessing'] = params('kaldi_pitch_post')
+    if with_cmvn:
+        config['cmvn'] = {
+            'by_speaker': True, 'with_vad': True, 'vad': params('vad')}
+    if with_delta:
+        config['delta'] = params('delta')
+    if to_yaml:
+        return _config_to_yaml(config, comments=yaml_commented)
+    return config
+
+
+class _Dumper(yaml.SafeDumper):
+    """Keeps the insertion order and knows the numpy scalar types"""
+
+
+_Dumper.add_representer(
+    dict, lambda d, data: d.represent_dict(data.items()))
+_Dumper.add_representer(
+    np.float32, lambda d, data: d.represent_float(float(data)))
+_Dumper.add_representer(
+    np.float64, lambda d, data: d.represent_float(float(data)))
+_Dumper.add_representer(
+    np.bool_, lambda d, data: d.represent_bool(bool(data)))
+
+
+def _config_to_yaml(config, comments=True):
+    """YAML rendering of a configuration, optionally commented with the
+    documentation of each parameter (shennong/pipeline.py:315-416)"""
+    text = yaml.dump(config, Dumper=_Dumper).strip()
+    if not comments:
+        return text + '\n'
+    out, stack, prev_indent = [], [], 0
+    for line in text.split('\n'):
+        key = line.split(': ')[0]
+        indent = len(key) - len(key.lstrip())
+        for _ in range((prev_indent - indent) // 2):
+            stack.pop()
+        if line.endswith(':'):
+            name = line[:-1].strip()
+            if name == 'postprocessing':
+                name = f'{stack[-1]}_post'
+            stack.append(name)
+            if name == 'vad' and indent != 4:
+                out.append(
+                    "  # The vad options are not used if 'with_vad' is false")
+            out.append(line)
+        else:
+            param, default = key.strip(), line.split(': ')[1].strip()
+            owner = stack[-1]
+            if owner == 'cmvn' and param == 'by_speaker':
+                doc = ('If false, do normalization by utterance, '
+                       'if true do normalization by speaker.')
+            elif owner == 'cmvn' and param == 'with_vad':
+                doc = ('If true do normalization only on frames where '
+                       'voice activity has been detected, if false do not '
+                       'consider voice activity for normalization.')
+            elif owner == 'pitch' and param == 'processor':
+                doc = f'Computing pitch using {default}'
+            elif 'pitch' in owner:
+                doc = PipelineManager.get_docstring(
+                    'kaldi_' + owner, param, default)
+            else:
+                doc = PipelineManager.get_docstring(owner, param, default)
+            out += [' ' * indent + '# ' + w
+                    for w in textwrap.wrap(doc, width=68 - indent)]
+            out.append(line)
+        prev_indent = indent
+    return '\n'.join(out) + '\n'
+
+
+def _init_config(config, log=get_logger('pipeline', 'warning')):
+    """Parses and validates a configuration (dict, YAML string or file)"""
+    try:
+        if os.path.isfile(config):
+            log.debug('loading configuration from %s', config)
+            with open(config, 'r') as stream:
+                config = stream.read()
+    except TypeError:
+        pass
+    if isinstance(config, str):
+        try:
+            config = yaml.load(config, Loader=yaml.FullLoader)
+        except yaml.YAMLError as err:
+            raise ValueError(f'error in configuration: {err}') from None
+    config = copy.deepcopy(config)
+    known = list(PipelineManager.valid_processors) + [
+        'pitch', 'bottleneck', 'vtln', 'ubm']
+    unknown = [k for k in config.keys() if k not in known]
+    if unknown:
+        raise ValueError(
+            'invalid keys in configuration: {}'.format(', '.join(unknown)))
+    for key in ('bottleneck', 'vtln', 'ubm'):
+        if key in config:
+            PipelineManager.get_processor_class(key)          # raises
+    features = [k for k in config.keys() if k in valid_features()]
+    if not features:
+        raise ValueError(
+            'the configuration does not define any features extraction '
+            '(must have one and only one entry of {})'
+            .format(', '.join(valid_features())))
+    if len(features) > 1:
+        raise ValueError(
+            'more than one features extraction processors are defined, '
+            '(must have one and only one entry of {}): {}'
+            .format(', '.join(valid_features()), ', '.join(features)))
+    if 'cmvn' in config:
+        if 'by_speaker' not in config['cmvn']:
+            log.warning(
+                'by_speaker option not specified for cmvn, '
+                'assuming it is false and doing cmvn by utterance')
+            config['cmvn']['by_speaker'] = False
+        config['cmvn'].setdefault('with_vad', True)
+        if config['cmvn']['with_vad']:
+            config['cmvn'].setdefault(
+                'vad', PipelineManager.get_processor_params('vad'))
+    if 'pitch' in config:
+        config['pitch'].setdefault('processor', 'kaldi')
+        config['pitch'].setdefault('postprocessing', {})
+    steps = []
+    if 'pitch' in config:
+        steps.append(f'{config["pitch"]["processor"]} pitch')
+    if 'delta' in config:
+        steps.append('delta')
+    if 'cmvn' in config:
+        steps.append('cmvn by {}{}'.format(
+            'speaker' if config['cmvn']['by_speaker'] else 'utterance',
+            ' with vad' if config['cmvn']['with_vad'] else ''))
+    log.info('pipeline configured for %s features extraction%s', features[0],
+             ' with {}'.format(', '.join(steps)) if steps else '')
+    return config
+
+
+def _init_warps(warps, config, utterances, log):
+    features = [k for k in config.keys() if k in valid_features()][0]
+    if features == 'spectrogram':
+        raise ValueError(f'{features} features do not support VTLN')
+    if warps.keys() == utterances.by_name().keys():
+        log.info('VTLN warps are defined by utterance')
+    elif (not utterances.has_speakers()
+          or warps.keys() != utterances.by_speaker().keys()):
+        raise ValueError(
+            'warps do not match utterances, either by speaker or by utterance')
+    else:
+        log.info('VTLN warps are defined by speaker')
+        warps = {utt.name: warps[utt.speaker] for utt in utterances}
+    return {name: float(warp) for name, warp in warps.items()}
+
+
+class _Carrier:
+    """Stands for a Features when only properties and ndims flow through the
+    processors' ``get_properties`` (the data itself stays on the device)"""
+    def __init__(self, properties, ndims):
+        self.properties = properties
+        self.ndims = ndims
+
+
+def extract_features(configuration, utterances, warps=None, njobs=1,
+                     log=get_logger('pipeline', 'warning')):
+    """Extracts the features of all the `utterances`
+
+    Parameters
+    ----------
+    configuration : dict or str
+        Pipeline configuration: a dict, a YAML string or the path to a YAML
+        file (see :func:`get_default_config`)
+    utterances : Utterances
+        The utterances to extract the features on
+    warps : dict, optional
+        Known VTLN warps indexed by utterance name or by speaker
+    njobs : int, optional
+        Host threads used to load the audio files (the extraction itself is
+        batched on the GPU)
+
+    Returns
+    -------
+    features : FeaturesCollection
+
+    Raises
+    ------
+    ValueError
+        On invalid configuration, utterances or warps
+    """
+    njobs = get_njobs(njobs, log=log)
+    config = _init_config(configuration, log=log)
+    log.info('detected format for utterances index is: %s',
+             utterances.format(type=str))
+    if warps:
+        warps = _init_warps(warps, config, utterances, log)
+    manager = PipelineManager(config, utterances, log=log)
+    if warps:
+        manager.warps = warps
+
+    utts = list(utterances)
+    if njobs > 1 and len(utts) > 1:
+        with concurrent.futures.ThreadPoolExecutor(njobs) as pool:
+            audios = list(pool.map(manager.get_audio, utts))
+    else:
+        audios = [manager.get_audio(u) for u in utts]
+
+    # one fused batch per sample rate (plans depend on it)
+    out = {}
+    rates = sorted(set(a.sample_rate for a in audios))
+    for rate in rates:
+        idx = [i for i, a in enumerate(audios) if a.sample_rate == rate]
+        out.update(_extract_group(
+            manager, [utts[i] for i in idx], [audios[i] for i in idx], log))
+    return FeaturesCollection((u.name, out[u.name]) for u in utts)
+
+
+def _extract_group(manager, utts, audios, log):
+    config = manager.config
+    proc = manager.get_features_processor(utts[0])
+    for audio in audios:
+        if audio.nchannels != 1:
+            raise ValueError(
+                'signal must have one dimension, but it has {}'.format(
+                    audio.nchannels))
+    delta = manager.get_delta_processor() if 'delta' in config else None
+    cmvn_mode, vad, energy = None, None, None
+    if 'cmvn' in config:
+        cmvn_mode = 'speaker' if config['cmvn']['by_speaker'] else 'utterance'
+        if config['cmvn']['with_vad']:
+            vad = manager.get_vad_processor()
+            energy = manager.get_energy_processor(utts[0])
+    pitch = None
+    if 'pitch' in config:
+        pitch = (manager.get_pitch_processor(utts[0]),
+                 manager.get_pitch_post_processor())
+        pitch[1]._validate(2)
+    has_warp = bool(manager.warps) and proc.name != 'spectrogram'
+    warps = ([manager.get_warp(u) for u in utts] if has_warp else None)
+    speakers = [u.speaker for u in utts]
+
+    # energy keeps the raw scale of float audio (energy.py:158): the fused
+    # path feeds int16 PCM to every processor, so VAD on non-int16 audio goes
+    # through the per-utterance API instead
+    raw_int16 = all(a.dtype == np.int16 for a in audios)
+    pcms = [a.astype(np.int16).data for a in audios]
+    packed = engine.PackedAudio(pcms)
+
+    def run(with_pitch, with_vad):
+        pipe = FusedPipeline(
+            proc, delta=delta, cmvn=cmvn_mode, norm_vars=True,
+            vad=vad if with_vad else None,
+            energy=energy if with_vad else None,
+            pitch=pitch if with_pitch else None)
+        dev, offs, stats, _ = pipe.run_device(
+            packed, speakers=speakers, warps=warps)
+        return pipe, engine.to_host(dev), offs, (
+            engine.to_host(stats) if stats is not None else None)
+
+    weights = None
+    if vad is not None and not raw_int16:
+        # rare path: per-utterance VAD weights from the host API
+        weights = []
+        for audio in audios:
+            v = vad.process(energy.process(audio))
+            weights.append(v.data.reshape(-1).astype(np.float32))
+    if weights is not None:
+        data, offs, stats, pipe = _run_with_weights(
+            proc, delta, cmvn_mode, packed, speakers, warps, weights)
+        pitch_blocks = _separate_pitch(pitch, audios) if pitch else None
+    else:
+        try:
+            pipe, data, offs, stats = run(pitch is not None, vad is not None)
+            pitch_blocks = None
+        except NotImplementedError:
+            # features and pitch disagree on the number of frames: paste
+            # with the reference's 2-frame tolerance on the host
+            pipe, data, offs, stats = run(False, vad is not None)
+            pitch_blocks = _separate_pitch(pitch, audios)
+
+    names = getattr(pipe, '_group_names', None)
+    result = {}
+    for i, (utt, audio) in enumerate(zip(utts, audios)):
+        block = data[offs[i]:offs[i + 1]]
+        warp = warps[i] if warps is not None else 1.0
+        props = (proc.get_properties() if proc.name == 'spectrogram'
+                 else proc.get_properties(vtln_warp=warp))
+        if utt.speaker:
+            props['speaker'] = utt.speaker
+        props['audio'] = {
+            'file': os.path.abspath(utt.audio_file),
+            'sample_rate': manager.audio_metadata[utt.audio_file].sample_rate}
+        if utt.tstart is not None:
+            props['audio']['tstart'] = utt.tstart
+            props['audio']['tstop'] = utt.tstop
+        props['audio']['duration'] = utt.duration
+        carrier = _Carrier(props, proc.ndims)
+        if cmvn_mode is not None:
+            cmvn = manager.get_cmvn_processor()
+            group = names.index(utt.speaker) if names is not None else i
+            cmvn.add_stats(stats[group])
+            if block.shape[0] and cmvn.count < 1.0:
+                raise ValueError(
+                    'insufficient accumulation of stats for CMVN, '
+                    'must be >= 1.0 but is {}'.format(cmvn.count))
+            carrier = _Carrier(cmvn.get_properties(carrier), proc.ndims)
+        if delta is not None:
+            carrier = _Carrier(delta.get_properties(carrier),
+                               proc.ndims * (delta.order + 1))
+        feat_dim = carrier.ndims
+        if pitch is not None and pitch_blocks is None:
+            pprops = pitch[1].get_properties(
+                _Carrier(pitch[0].get_properties(), 2))
+            props = carrier.properties
+            props.update(
+                {k: v for k, v in pprops.items() if k != 'pipeline'})
+            for entry in pprops['pipeline']:
+                entry['columns'] = [c + feat_dim for c in entry['columns']]
+                props['pipeline'].append(entry)
+            feats = Features(block, proc.times(block.shape[0]), props)
+        else:
+            feats = Features(
+                block[:, :feat_dim], proc.times(block.shape[0]),
+                carrier.properties)
+            if pitch_blocks is not None:
+                feats = feats.concatenate(pitch_blocks[i], tolerance=2,
+                                          log=log)
+        result[utt.name] = feats
+    return result
+
+
+def _separate_pitch(pitch, audios):
+    raw = pitch[0]._process_batch(audios)
+    return [pitch[1].process(r) for r in raw]
+
+
+def _run_with_weights(proc, delta, cmvn_mode, packed, speakers, warps,
+                      weights):
+    """CMVN weighted by host-provided VAD decisions"""
+    torch = engine.require_cuda()
+    pipe = FusedPipeline(proc, delta=delta, cmvn=None)
+    plans = pipe._plans()
+    batch = engine.Batch(plans['feat'], packed, warps)
+    layout = engine.RowLayout(batch=batch)
+    seed = engine.next_seed() if proc.dither != 0 else 0
+    base = engine.compute_features(plans['feat'], batch, seed=seed)
+    w = engine.from_host(np.concatenate(weights), np.float32)
+    stats = engine.cmvn_accumulate(base, layout, w)
+    utt_group = None
+    if cmvn_mode == 'speaker':
+        names = sorted(set(speakers))
+        group = np.array([names.index(s) for s in speakers], dtype=np.int64)
+        ptr = np.concatenate(
+            ([0], np.cumsum(np.bincount(group, minlength=len(names)))))
+        stats = engine.cmvn_reduce_groups(
+            stats, ptr, np.argsort(group, kind='stable'), len(names))
+        utt_group = torch.from_numpy(group.astype(np.int32)).to('cuda')
+        pipe._group_names = names
+    norm = engine.cmvn_norm(stats, True, False)
+    order = delta.order if delta is not None else 0
+    window = delta.window if delta is not None else 1
+    out = engine.deltas(base, layout, order, window, norm=norm,
+                        utt_group=utt_group)
+    return (engine.to_host(out), batch.frame_offsets, engine.to_host(stats),
+            pipe)

@@ -1,0 +1,155 @@
+"""pipeline.extract_features on the GPU: equals the composition of the
+individual processors (the reference's schedule, pipeline.py:570-648) and
+produces the same properties layout (test/test_pipeline.py:276-420)."""
+
+import numpy as np
+import pytest
+import scipy.io.wavfile
+
+import oracle
+from conftest import scale_close, synth_utterance
+from shennong_b200 import Audio, Utterances, pipeline
+from shennong_b200.postprocessor import (
+    CmvnPostProcessor, DeltaPostProcessor, VadPostProcessor)
+from shennong_b200.processor import (
+    EnergyProcessor, KaldiPitchPostProcessor, KaldiPitchProcessor,
+    MfccProcessor)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def corpus(tmp_path_factory, pcm):
+    root = tmp_path_factory.mktemp('wavs')
+    entries = []
+    lengths = [22713, 48000, 16000, 31000]
+    for i, n in enumerate(lengths):
+        data = pcm if i == 0 else synth_utterance(i, n)
+        path = root / f'w{i}.wav'
+        scipy.io.wavfile.write(path, 16000, data)
+        entries.append((f'utt{i}', str(path), f'spk{i % 2}'))
+    # a segment of the first file
+    entries.append(('utt4', entries[0][1], 'spk0', 0.2, 1.2))
+    return entries
+
+
+def no_dither(config):
+    for key in ('mfcc', 'filterbank', 'plp', 'spectrogram'):
+        if key in config:
+            config[key]['dither'] = 0
+    if 'pitch' in config:
+        config['pitch']['postprocessing']['delta_pitch_noise_stddev'] = 0
+    return config
+
+
+@pytest.mark.parametrize('features', ['mfcc', 'filterbank', 'plp',
+                                      'spectrogram'])
+@pytest.mark.parametrize('with_delta', [False, True])
+def test_features_and_delta(corpus, features, with_delta):
+    config = no_dither(pipeline.get_default_config(
+        features, with_delta=with_delta))
+    utts = Utterances([e[:2] for e in corpus[:3]])
+    feats = pipeline.extract_features(config, utts, njobs=2)
+    assert list(feats.keys()) == ['utt0', 'utt1', 'utt2']
+    proc = pipeline.PipelineManager.get_processor_class(features)(
+        **config[features])
+    for name, path in [e[:2] for e in corpus[:3]]:
+        ref = proc.process(Audio.load(path))
+        if with_delta:
+            ref = DeltaPostProcessor().process(ref)
+        got = feats[name]
+        assert got.shape == ref.shape
+        assert np.allclose(got.data, ref.data, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(got.times, ref.times)
+        assert got.properties['pipeline'] == ref.properties['pipeline']
+        assert set(got.properties) == set(ref.properties) | {'audio'}
+        assert got.properties['audio']['sample_rate'] == 16000
+    assert feats['utt0'].shape[0] == 140
+
+
+@pytest.mark.parametrize('by_speaker', [True, False])
+@pytest.mark.parametrize('with_vad', [True, False])
+def test_cmvn_delta_pitch_full_pipeline(corpus, by_speaker, with_vad):
+    config = no_dither(pipeline.get_default_config(
+        'mfcc', with_pitch='kaldi', with_cmvn=True, with_delta=True))
+    config['cmvn']['by_speaker'] = by_speaker
+    config['cmvn']['with_vad'] = with_vad
+    utts = Utterances(corpus)
+    feats = pipeline.extract_features(config, utts, njobs=2)
+    assert set(feats.keys()) == {e[0] for e in corpus}
+
+    # the reference's schedule with the individual processors
+    mfcc, energy, vad = (MfccProcessor(dither=0), EnergyProcessor(dither=0),
+                         VadPostProcessor())
+    base, weights = {}, {}
+    for utt in utts:
+        audio = utt.load_audio()
+        base[utt.name] = mfcc.process(audio)
+        if with_vad:
+            weights[utt.name] = vad.process(
+                energy.process(audio)).data.reshape(-1).astype(np.float32)
+    groups = {}
+    for utt in utts:
+        groups.setdefault(utt.speaker if by_speaker else utt.name,
+                          []).append(utt.name)
+    for members in groups.values():
+        cmvn = CmvnPostProcessor(13)
+        for name in members:
+            cmvn.accumulate(base[name], weights.get(name))
+        for name in members:
+            ref = DeltaPostProcessor().process(cmvn.process(base[name]))
+            got = feats[name]
+            assert got.shape == (ref.shape[0], 42)
+            scale_close(got.data[:, :39], ref.data, tol=2e-4)
+            assert np.allclose(
+                got.properties['cmvn']['stats'], cmvn.stats, rtol=1e-6)
+    # pitch columns and properties
+    for utt in utts:
+        audio = utt.load_audio()
+        raw = KaldiPitchProcessor().process(audio)
+        post = KaldiPitchPostProcessor(delta_pitch_noise_stddev=0).process(raw)
+        got = feats[utt.name]
+        assert np.allclose(got.data[:, 39:], post.data, atol=1e-5)
+        assert set(got.properties.keys()) == {
+            'audio', 'mfcc', 'cmvn', 'pitch', 'delta', 'speaker', 'pipeline'}
+        assert got.properties['pipeline'] == [
+            {'name': 'mfcc', 'columns': [0, 12]},
+            {'name': 'cmvn', 'columns': [0, 12]},
+            {'name': 'delta', 'columns': [0, 38]},
+            {'name': 'pitch', 'columns': [39, 41]}]
+        assert 'pitch postprocessing' in got.properties['pitch']
+    assert feats['utt4'].properties['audio']['tstart'] == 0.2
+    assert feats['utt4'].shape[0] == 98               # 1 s crop
+    # CMVN'd base columns have zero mean per group when VAD is off
+    if not with_vad and not by_speaker:
+        for f in feats.values():
+            assert np.abs(f.data[:, :13].mean(0)).max() < 1e-4
+
+
+def test_vtln_warps_and_save_load(corpus, tmp_path):
+    config = no_dither(pipeline.get_default_config('mfcc'))
+    utts = Utterances([e[:3] for e in corpus[:4]])
+    by_spk = pipeline.extract_features(
+        config, utts, warps={'spk0': 0.9, 'spk1': 1.1})
+    by_utt = pipeline.extract_features(
+        config, utts, warps={'utt0': 0.9, 'utt1': 1.1, 'utt2': 0.9,
+                             'utt3': 1.1})
+    assert by_spk == by_utt
+    for name, path, spk in [e[:3] for e in corpus[:4]]:
+        warp = 0.9 if spk == 'spk0' else 1.1
+        ref = oracle.features(
+            'mfcc', Audio.load(path).data, vtln_warp=warp)
+        scale_close(by_spk[name].data, ref, tol=1e-4)
+        assert by_spk[name].properties['mfcc']['vtln_warp'] == warp
+    with pytest.raises(ValueError):
+        pipeline.extract_features(config, utts, warps={'nobody': 1.0})
+    for ext in ('.pkl', '.npz'):
+        path = tmp_path / f'feats{ext}'
+        by_spk.save(str(path))
+        assert type(by_spk).load(str(path)) == by_spk
+
+
+def test_errors(corpus):
+    config = pipeline.get_default_config('mfcc', with_cmvn=True)
+    with pytest.raises(ValueError, match='no speaker information'):
+        pipeline.extract_features(config, Utterances([e[:2] for e in corpus[:2]]))
