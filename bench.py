@@ -318,6 +318,16 @@ def main():
         out_host = torch.empty((total_frames, 39), dtype=torch.float32,
                                pin_memory=True)
         torch.cuda.synchronize()
+        # raw PCIe ceilings of this box (plain pinned copies, one direction)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scratch = torch.empty_like(pcm_dev)
+        c0.record(); scratch.copy_(host_pcm, non_blocking=True); c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = host_pcm.numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        c0.record(); out_host.copy_(out, non_blocking=True); c1.record()
+        torch.cuda.synchronize()
+        d2h_gbs = out.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del scratch
         nrep = max(2, min(args.steps, 5))
         pipe.run_host(host_pcm, starts, lengths, out_host=out_host)  # warm-up
         barrier()
@@ -334,7 +344,8 @@ def main():
                'h2d_bytes_per_step': int(nutts * UTT_SAMPLES * 2),
                'd2h_bytes_per_step': int(total_frames * 39 * 4),
                'ms_per_step': dt * 1e3,
-               'api': 'FusedPipeline.run_host (chunked H2D/compute/D2H)'}
+               'api': 'FusedPipeline.run_host (chunked H2D/compute/D2H)',
+               'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs}
 
     if rank != 0:
         if world > 1:

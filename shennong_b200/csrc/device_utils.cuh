@@ -88,6 +88,30 @@ __device__ __forceinline__ void gauss_pair(uint64_t seed, uint64_t frame,
   *g1 = r * s;
 }
 
+// cheaper variant for the fused fast path: one 32-bit hash per PAIR of samples
+// (16 bits per uniform: |g| <= 4.86), MUFU-only Box-Muller
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t frame_noise_key(uint64_t seed, uint64_t frame) {
+  const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+  return hash32(hash32(static_cast<uint32_t>(frame) ^ lo) + static_cast<uint32_t>(frame >> 32)) ^ hi;
+}
+__device__ __forceinline__ void gauss_pair_fast(uint32_t key, uint32_t pair, float *g0, float *g1) {
+  const uint32_t h = hash32(key + pair * 0x9e3779b9u);
+  const float u1 = (static_cast<float>(h >> 16) + 0.5f) * (1.0f / 65536.0f);   // (0,1)
+  const float u2 = static_cast<float>(h & 0xffffu) * (1.0f / 65536.0f);        // [0,1)
+  const float t = -2.0f * __logf(u1);          // > 0
+  const float r = t * rsqrtf(t);               // sqrt(t)
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  *g0 = r * c;
+  *g1 = r * s;
+}
+
 // ---- complex helpers ---------------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);

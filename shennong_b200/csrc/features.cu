@@ -19,6 +19,7 @@
 // pair computed once), then warp-local mel / log / DCT / PLP tails.
 // Generic path (any other FFT size, incl. non powers of two): one warp per
 // frame, shared-memory radix-2 FFT or direct DFT, same tails.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -39,15 +40,26 @@ __device__ __forceinline__ int64_t first_sample_of_frame_dev(int64_t frame, cons
 struct MelView {          // decoded mel blob (in shared or global memory)
   const int32_t *first, *size, *offset;
   const float *loudness, *weights;
+  // segment tables (see MelBanksHost): used by the 16-lane fast path
+  const int32_t *seg_first, *seg_size, *lane_seg;
+  const float2 *updown;
+  int nslots;
 };
 
-__device__ __forceinline__ MelView mel_view(const int32_t *blob, int B) {
+__device__ __forceinline__ MelView mel_view(const int32_t *blob, const FeatParams &p) {
+  const int B = p.B;
   MelView v;
   v.first = blob;
   v.size = blob + B;
   v.offset = blob + 2 * B;
   v.loudness = reinterpret_cast<const float *>(blob + 3 * B);
   v.weights = reinterpret_cast<const float *>(blob + 4 * B);
+  const int32_t *seg = blob + p.mel_seg_off;
+  v.seg_first = seg;
+  v.seg_size = seg + (B + 1);
+  v.lane_seg = seg + 2 * (B + 1);
+  v.nslots = p.mel_nslots;
+  v.updown = reinterpret_cast<const float2 *>(blob + p.mel_updown_off);
   return v;
 }
 
@@ -84,14 +96,48 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
     for (int k = gl; k <= half; k += G) P[k] = sqrtf(P[k]);
     __syncwarp();
   }
-  // mel energies: lane-per-bin sparse dot products
+  // mel energies
   float *mel = scratch;  // [B+2]; PLP uses mel[1..B] with duplicated ends
   const int moff = (xo.kind == SNB_FEAT_PLP) ? 1 : 0;
+  float *useg = scratch + (B + 2) + (xo.lpc_order + 2);   // [B+1] rising sums
+  float *dseg = useg + (B + 1);                            // [B+1] falling sums
+  if (G == 16) {
+    // segment form: every FFT bin is visited once and feeds (up, down) of its
+    // segment; segments are dealt to the lanes by decreasing size (host LPT)
+    for (int slot = 0; slot < t.mel.nslots; ++slot) {
+      const int sgm = t.mel.lane_seg[slot * 16 + gl];
+      if (sgm >= 0) {
+        const int first = t.mel.seg_first[sgm], size = t.mel.seg_size[sgm];
+        const float2 *w = t.mel.updown + first;
+        const float *pp = P + first;
+        float u = 0.0f, d = 0.0f;
+        int i = 0;
+        for (; i + 1 < size; i += 2) {
+          const float2 w0 = w[i], w1 = w[i + 1];
+          const float p0 = pp[i], p1 = pp[i + 1];
+          u = fmaf(w0.x, p0, u); d = fmaf(w0.y, p0, d);
+          u = fmaf(w1.x, p1, u); d = fmaf(w1.y, p1, d);
+        }
+        if (i < size) {
+          const float2 w0 = w[i];
+          const float p0 = pp[i];
+          u = fmaf(w0.x, p0, u); d = fmaf(w0.y, p0, d);
+        }
+        useg[sgm] = u;
+        dseg[sgm] = d;
+      }
+    }
+    __syncwarp();
+  }
   for (int b = gl; b < B; b += G) {
-    const int first = t.mel.first[b], size = t.mel.size[b];
-    const float *w = t.mel.weights + t.mel.offset[b];
     float acc = 0.0f;
-    for (int i = 0; i < size; ++i) acc = fmaf(w[i], P[first + i], acc);
+    if (G == 16) {
+      acc = useg[b] + dseg[b + 1];
+    } else {
+      const int first = t.mel.first[b], size = t.mel.size[b];
+      const float *w = t.mel.weights + t.mel.offset[b];
+      for (int i = 0; i < size; ++i) acc = fmaf(w[i], P[first + i], acc);
+    }
     if (xo.kind == SNB_FEAT_FBANK) {
       if (xo.use_log_fbank) acc = logf(fmaxf(acc, FLT_EPSILON));
       const int off = (xo.use_energy && !xo.htk_compat) ? 1 : 0;
@@ -133,7 +179,7 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
   const int L = xo.lpc_order;       // <= G - 1 (checked at plan creation)
   if (gl == 0) { mel[0] = mel[1]; mel[B + 1] = mel[B]; }
   __syncwarp();
-  float *ac = scratch + (B + 2);    // [L+1]
+  float *ac = scratch + (B + 2);    // [L+1] (useg/dseg follow at B+2 + L+2)
   for (int i = gl; i <= L; i += G) {
     const float *row = t.idft + i * (B + 2);
     float acc = 0.0f;
@@ -274,10 +320,11 @@ fused_features_512_kernel(const FastArgs a) {
   uint32_t parity = 0;
   TailTables tt;
   tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
-  tt.mel = mel_view(s_mel, B);
+  tt.mel = mel_view(s_mel, p);
 
   const bool pair_ok_static = (S % 2) == 0;
   const float dither = p.fo.dither;
+  const int nfull = W / 32;           // n1 iterations with 32 valid samples
 
   for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const TileDesc td = a.tiles[tile];
@@ -334,24 +381,37 @@ fused_features_512_kernel(const FastArgs a) {
       const bool pair_ok = pair_ok_static && ((mis & 1) == 0);
       float xr[16], xi[16];
       // ---- load + int16 -> float (+ dither) ----
+      // n1 < nfull: every lane holds two valid samples; n1 == nfull: the
+      // ragged tail (W % 32 samples); beyond: zero padding up to 512
       float lsum = 0.0f;
+      uint32_t dither_base = 0;
+      if (dither != 0.0f) dither_base = frame_noise_key(a.seed, static_cast<uint64_t>(row0 + fidx));
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const int i0 = 2 * (16 * n1 + hl);
         float v0 = 0.0f, v1 = 0.0f;
-        if (i0 < W) {
-          if (pair_ok && i0 + 1 < W) {
+        if (n1 < nfull) {
+          if (pair_ok) {
             const int32_t pr = *reinterpret_cast<const int32_t *>(fr + i0);
             v0 = static_cast<float>(static_cast<int16_t>(pr & 0xffff));
             v1 = static_cast<float>(pr >> 16);
           } else {
             v0 = static_cast<float>(fr[i0]);
-            if (i0 + 1 < W) v1 = static_cast<float>(fr[i0 + 1]);
+            v1 = static_cast<float>(fr[i0 + 1]);
           }
           if (dither != 0.0f) {
             float g0, g1;
-            gauss_pair(a.seed, static_cast<uint64_t>(row0 + fidx), i0 >> 1, &g0, &g1);
+            gauss_pair_fast(dither_base, 16 * n1 + hl, &g0, &g1);
             v0 = fmaf(dither, g0, v0);
+            v1 = fmaf(dither, g1, v1);
+          }
+        } else if (n1 == nfull) {
+          if (i0 < W) v0 = static_cast<float>(fr[i0]);
+          if (i0 + 1 < W) v1 = static_cast<float>(fr[i0 + 1]);
+          if (dither != 0.0f) {
+            float g0, g1;
+            gauss_pair_fast(dither_base, 16 * n1 + hl, &g0, &g1);
+            if (i0 < W) v0 = fmaf(dither, g0, v0);
             if (i0 + 1 < W) v1 = fmaf(dither, g1, v1);
           }
         }
@@ -363,9 +423,13 @@ fused_features_512_kernel(const FastArgs a) {
         const float mean = __fdiv_rn(group_sum<16>(lsum), static_cast<float>(W));
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-          const int i0 = 2 * (16 * n1 + hl);
-          if (i0 < W) xr[n1] -= mean;
-          if (i0 + 1 < W) xi[n1] -= mean;
+          if (n1 < nfull) {
+            xr[n1] -= mean; xi[n1] -= mean;
+          } else if (n1 == nfull) {
+            const int i0 = 2 * (16 * n1 + hl);
+            if (i0 < W) xr[n1] -= mean;
+            if (i0 + 1 < W) xi[n1] -= mean;
+          }
         }
       }
       // ---- raw log-energy / float64 energy ----
@@ -534,7 +598,7 @@ generic_features_kernel(const GenArgs a) {
     const int64_t n = a.sample_len[utt];
     const int64_t start = first_sample_of_frame_dev(f, p);
     if (B > 0)
-      tt.mel = mel_view(a.mel_blobs + static_cast<int64_t>(a.utt_mel_idx[utt]) * p.mel_blob_stride, B);
+      tt.mel = mel_view(a.mel_blobs + static_cast<int64_t>(a.utt_mel_idx[utt]) * p.mel_blob_stride, p);
     __syncwarp();
     // load (reflect at edges), dither
     float lsum = 0.0f;
@@ -654,7 +718,7 @@ static void fast_layout(const snb_plan *plan, FastSmemLayout *sm) {
   sm->mel = off; off += align_up(p.mel_blob_stride * 4, 16);
   sm->span_cap = align_up((plan->tile_frames - 1) * p.S + p.W + 16, 8);
   sm->pcm = off; off += align_up(sm->span_cap * 2, 16);
-  sm->grp_floats = align_up(std::max(16 * kXStride * 2, 272 + p.B + 2 + xo.lpc_order + 2), 4);
+  sm->grp_floats = align_up(std::max(16 * kXStride * 2, 272 + (p.B + 2) + (xo.lpc_order + 2) + 2 * (p.B + 2)), 4);
   sm->grp = off; off += kFastGroups * sm->grp_floats * 4;
   sm->bar = off; off += 16;
   sm->total = off;
@@ -685,7 +749,7 @@ int feature_plan_finalize(snb_plan *plan) {
   plan->tile_frames = 1;
   const int tables = (xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * p.B : 0) + xo.num_ceps +
                      (xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0);
-  const int warp_floats = 2 * p.N + p.B + 2 + xo.lpc_order + 2 + 8;
+  const int warp_floats = 2 * p.N + 3 * (p.B + 2) + xo.lpc_order + 2 + 8;
   plan->smem_bytes = static_cast<size_t>(align_up(tables, 4) + kGenWarps * align_up(warp_floats, 4)) * 4;
   if (plan->smem_bytes > 220 * 1024)
     return set_error(SNB_ERR_UNSUPPORTED, "options need too much shared memory");
@@ -716,6 +780,32 @@ static int get_mel_blob(const snb_plan *plan, float warp, const std::vector<int3
       std::memcpy(&blob[3 * B + b], &loud[b], 4);
     }
     std::memcpy(&blob[4 * B], mb.weights.data(), mb.weights.size() * 4);
+    // segment tables + longest-processing-time dealing of segments to lanes
+    int32_t *seg = blob.data() + p.mel_seg_off;
+    for (int sg = 0; sg <= B; ++sg) {
+      seg[sg] = mb.seg_first[sg];
+      seg[(B + 1) + sg] = mb.seg_size[sg];
+    }
+    int32_t *lane_seg = seg + 2 * (B + 1);
+    for (int i = 0; i < p.mel_nslots * 16; ++i) lane_seg[i] = -1;
+    std::vector<int> order(B + 1);
+    for (int i = 0; i <= B; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b2) { return mb.seg_size[a] > mb.seg_size[b2]; });
+    int load[16] = {0}, used[16] = {0};
+    for (int sg : order) {
+      int best = -1;
+      for (int l = 0; l < 16; ++l)
+        if (used[l] < p.mel_nslots && (best < 0 || load[l] < load[best])) best = l;
+      lane_seg[used[best] * 16 + best] = sg;
+      used[best] += 1;
+      load[best] += mb.seg_size[sg] + 2;
+    }
+    const int updown_off = p.mel_updown_off;
+    for (int i = 0; i < mb.num_fft_bins; ++i) {
+      std::memcpy(&blob[updown_off + 2 * i], &mb.up[i], 4);
+      std::memcpy(&blob[updown_off + 2 * i + 1], &mb.down[i], 4);
+    }
     it = plan->mel_blobs.emplace(key, std::move(blob)).first;
   }
   *out = &it->second;
@@ -797,7 +887,12 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
   // validate the mel options now (KALDI_ERR at construction of the computer)
   if (needs_mel) {
     p.mel_wcap = 2 * (p.N / 2) + 2 * p.B + 8;
-    p.mel_blob_stride = 4 * p.B + p.mel_wcap;
+    p.mel_seg_off = 4 * p.B + p.mel_wcap;
+    p.mel_nslots = (p.B + 1 + 15) / 16;
+    p.mel_updown_off = p.mel_seg_off + 2 * (p.B + 1) + p.mel_nslots * 16;
+    p.mel_updown_off += p.mel_updown_off & 1;
+    p.mel_blob_stride = p.mel_updown_off + 2 * (p.N / 2) + 2;
+    p.mel_blob_stride += p.mel_blob_stride & 1;
     const std::vector<int32_t> *blob;
     rc = get_mel_blob(plan, 1.0f, &blob);
     if (rc != SNB_OK) return fail(rc);
@@ -1085,7 +1180,7 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
   const int tables = (xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * p.B : 0) + xo.num_ceps +
                      (xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0);
   g.tables_floats = align_up(tables, 4);
-  g.warp_floats = align_up(2 * p.N + p.B + 2 + xo.lpc_order + 2 + 8, 4);
+  g.warp_floats = align_up(2 * p.N + 3 * (p.B + 2) + xo.lpc_order + 2 + 8, 4);
   g.sample_begin = batch->d_sample_begin;
   g.sample_len = batch->d_sample_len;
   g.frame_offsets = batch->d_frame_offsets;

@@ -4,6 +4,7 @@
 // sliding-window CMN (cmvn.py:492), energy VAD (postprocessor/vad.py:183).
 // These are HBM-bound: each input element is read once from DRAM (neighbour
 // rows come from L1/L2), each output written once, rows are coalesced.
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <vector>
@@ -81,6 +82,71 @@ __global__ void __launch_bounds__(256) delta_kernel(const DeltaArgs a) {
         acc = fmaf(s, x, acc);
       }
       o[i * dim + d] = acc;
+    }
+  }
+}
+
+// Tiled variant (halo <= 16 rows): a CTA stages kTileRows + 2*halo NORMALISED
+// rows in shared memory with coalesced loads (each input element is read once
+// from global memory and normalised once), then every warp writes whole output
+// rows (coalesced) from shared-memory taps.
+constexpr int kTileRows = 64;
+constexpr int kMaxHalo = 16;
+
+__global__ void __launch_bounds__(256) delta_tiled_kernel(const DeltaArgs a, const int halo) {
+  extern __shared__ float s_x[];                        // [nload, dim]
+  __shared__ int64_t s_first[kTileRows + 2 * kMaxHalo], s_last[kTileRows + 2 * kMaxHalo];
+  __shared__ int32_t s_group[kTileRows + 2 * kMaxHalo];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dim = a.dim, odim = a.dim * (a.order + 1);
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kTileRows;
+  const int64_t lo = row0 - halo;
+  const int nload = kTileRows + 2 * halo;
+  const int nrows = static_cast<int>(min(static_cast<int64_t>(kTileRows), a.total_frames - row0));
+  for (int i = tid; i < nload; i += 256) {
+    const int64_t t = lo + i;
+    if (t >= 0 && t < a.total_frames) {
+      const int64_t u = find_utt_row(a.frame_offsets, a.nutts, t);
+      s_first[i] = a.frame_offsets[u];
+      s_last[i] = a.frame_offsets[u + 1] - 1;
+      s_group[i] = a.utt_group ? a.utt_group[u] : static_cast<int32_t>(u);
+    } else {
+      s_first[i] = 0; s_last[i] = -1; s_group[i] = 0;
+    }
+  }
+  __syncthreads();
+  const bool do_norm = a.norm != nullptr;
+  for (int i = warp; i < nload; i += 8) {
+    const int64_t t = lo + i;
+    const bool ok = s_last[i] >= s_first[i];
+    const float *n = do_norm ? a.norm + static_cast<int64_t>(s_group[i]) * 2 * dim : nullptr;
+    for (int d = lane; d < dim; d += 32) {
+      float x = 0.0f;
+      if (ok) {
+        x = a.in[t * a.ld_in + d];
+        if (do_norm) x = __fadd_rn(__fmul_rn(x, n[dim + d]), n[d]);
+      }
+      s_x[i * dim + d] = x;
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < nrows; r += 8) {
+    const int64_t t = row0 + r, first = s_first[r + halo], last = s_last[r + halo];
+    float *o = a.out + t * a.ld_out;
+    for (int c = lane; c < odim; c += 32) {
+      int ord = 0, d = c;
+      while (d >= dim) { d -= dim; ++ord; }
+      const int half = a.tap_half[ord];
+      const float *taps = a.taps + a.tap_off[ord];
+      float acc = 0.0f;
+      for (int j = -half; j <= half; ++j) {
+        const float s = taps[j + half];
+        if (s == 0.0f) continue;
+        int64_t tt = t + j;
+        tt = tt < first ? first : (tt > last ? last : tt);
+        acc = fmaf(s, s_x[static_cast<int>(tt - lo) * dim + d], acc);
+      }
+      o[c] = acc;
     }
   }
 }
@@ -320,7 +386,22 @@ extern "C" int snb_cmvn_apply_deltas(const float *d_in, int64_t ld_in, int32_t d
   a.frame_offsets = d_frame_offsets; a.nutts = nutts; a.total_frames = total_frames;
   a.norm = d_norm; a.utt_group = d_utt_group;
   a.out = d_out; a.ld_out = ld_out;
-  delta_kernel<<<row_ctas(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const int halo = a.tap_half[a.order];
+  const size_t smem = static_cast<size_t>(kTileRows + 2 * halo) * dim * sizeof(float);
+  if (halo <= kMaxHalo && smem <= 96 * 1024) {
+    static std::atomic<size_t> cur{48 * 1024};
+    size_t c = cur.load();
+    while (smem > c) {
+      cudaError_t e = cudaFuncSetAttribute(delta_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "delta smem: %s", cudaGetErrorString(e));
+      if (cur.compare_exchange_weak(c, smem)) break;
+    }
+    const unsigned ctas = static_cast<unsigned>((total_frames + kTileRows - 1) / kTileRows);
+    delta_tiled_kernel<<<ctas, 256, smem, static_cast<cudaStream_t>(stream)>>>(a, halo);
+  } else {
+    delta_kernel<<<row_ctas(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -56,6 +56,11 @@ struct MelBanksHost {
   std::vector<float> weights;           // concatenated ranges
   std::vector<int32_t> offset;          // start of each range in weights
   std::vector<float> center_freqs;
+  // segment view: segment s in [0, B] holds the FFT bins whose mel value lies
+  // in (center[s-1], center[s]]; such a bin feeds the rising side of
+  // triangle s (weight up) and the falling side of triangle s-1 (weight down)
+  std::vector<int32_t> seg_first, seg_size;   // [B+1]
+  std::vector<float> up, down;                // [num_fft_bins]
 };
 // returns SNB_OK or SNB_ERR_OPTION (sets error)
 int build_mel_banks(const snb_frame_opts &fo, const snb_mel_opts &mo,
@@ -88,6 +93,9 @@ struct FeatParams {
   int32_t dim;                // output columns
   int32_t mel_blob_stride;    // in 4-byte words
   int32_t mel_wcap;           // weights capacity per blob
+  int32_t mel_seg_off;        // word offset of the segment tables in a blob
+  int32_t mel_nslots;         // segments per lane (16-lane groups)
+  int32_t mel_updown_off;     // word offset (even) of the float2 (up, down) table
   int32_t need_raw_energy, need_post_energy;
   float log_energy_floor;
   float eps_energy;           // FLT_EPSILON (Kaldi) or DBL_EPSILON (plp.py)

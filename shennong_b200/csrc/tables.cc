@@ -150,6 +150,11 @@ int build_mel_banks(const snb_frame_opts &fo, const snb_mel_opts &mo,
   out->offset.assign(B, 0);
   out->center_freqs.assign(B, 0.0f);
   out->weights.clear();
+  out->seg_first.assign(B + 1, 0);
+  out->seg_size.assign(B + 1, 0);
+  out->up.assign(nfft, 0.0f);
+  out->down.assign(nfft, 0.0f);
+  std::vector<int32_t> seg_of(nfft, -1);
   std::vector<float> bin_mel(nfft);
   for (int32_t i = 0; i < nfft; ++i) bin_mel[i] = hz_to_mel(bin_width * i);
   for (int32_t b = 0; b < B; ++b) {
@@ -177,11 +182,33 @@ int build_mel_banks(const snb_frame_opts &fo, const snb_mel_opts &mo,
     for (int32_t i = first; i <= last; ++i) {
       const float m = bin_mel[i];
       float w = 0.0f;
-      if (m > left && m < right)
-        w = m <= center ? (m - left) / (center - left)
-                        : (right - m) / (right - center);
+      if (m > left && m < right) {
+        if (m <= center) {
+          w = (m - left) / (center - left);
+          out->up[i] = w;
+          seg_of[i] = b;
+        } else {
+          w = (right - m) / (right - center);
+          out->down[i] = w;
+          seg_of[i] = b + 1;
+        }
+      }
       out->weights.push_back(w);
     }
+  }
+  // segments are contiguous runs of FFT bins (mel is increasing with i)
+  for (int32_t s = 0; s <= B; ++s) {
+    int32_t first = -1, last = -1;
+    for (int32_t i = 0; i < nfft; ++i)
+      if (seg_of[i] == s) {
+        if (first < 0) first = i;
+        last = i;
+      }
+    out->seg_first[s] = first < 0 ? 0 : first;
+    out->seg_size[s] = first < 0 ? 0 : last + 1 - first;
+    for (int32_t i = out->seg_first[s]; i < out->seg_first[s] + out->seg_size[s]; ++i)
+      if (seg_of[i] != s)
+        return set_error(SNB_ERR_UNSUPPORTED, "non monotonic mel segments");
   }
   return SNB_OK;
 }
