@@ -995,100 +995,102 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
     b->frame_offsets[u + 1] = b->frame_offsets[u] + nf;
   }
   b->total_frames = b->frame_offsets[nutts];
-  cudaError_t e = cudaMalloc(&b->d_sample_begin, (nutts + 1) * sizeof(int64_t));
-  if (e == cudaSuccess) e = cudaMalloc(&b->d_sample_len, (nutts + 1) * sizeof(int64_t));
-  if (e == cudaSuccess) e = cudaMalloc(&b->d_frame_offsets, (nutts + 1) * sizeof(int64_t));
-  if (e == cudaSuccess && nutts > 0)
-    e = upload(b->d_sample_begin, b->sample_begin.data(), nutts * sizeof(int64_t));
-  if (e == cudaSuccess && nutts > 0)
-    e = upload(b->d_sample_len, b->sample_len.data(), nutts * sizeof(int64_t));
-  if (e == cudaSuccess)
-    e = upload(b->d_frame_offsets, b->frame_offsets.data(), (nutts + 1) * sizeof(int64_t));
-  if (e != cudaSuccess)
-    return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
+  // every device-side table of the batch lives in ONE allocation filled by
+  // ONE upload (16-byte aligned sections): batch creation costs a single
+  // cudaMalloc + one host->device copy
+  std::vector<unsigned char> stage;
+  auto add_section = [&](const void *src, size_t bytes) {
+    const size_t off = (stage.size() + 15) / 16 * 16;
+    stage.resize(off + bytes);
+    if (bytes) std::memcpy(stage.data() + off, src, bytes);
+    return off;
+  };
+  const size_t o_begin = add_section(b->sample_begin.data(), nutts * sizeof(int64_t));
+  const size_t o_len = add_section(b->sample_len.data(), nutts * sizeof(int64_t));
+  const size_t o_foff = add_section(b->frame_offsets.data(), (nutts + 1) * sizeof(int64_t));
+  size_t o_down = 0, o_mel = 0, o_tiles = 0;
+  bool has_down = false, has_mel = false, has_tiles = false;
   if (plan->kind == 1) {
     int rc = pitch_batch_init(plan, b);
     if (rc != SNB_OK) return fail(rc);
-    *out = b;
-    return SNB_OK;
-  }
-  // ---- mel blobs for the distinct VTLN warps of this batch ----
-  std::vector<int32_t> utt_mel(nutts, 0);
-  std::vector<int32_t> blobs;
-  if (plan->has_mel) {
-    std::map<uint32_t, int32_t> index;
-    for (int64_t u = 0; u < nutts; ++u) {
-      const float w = vtln_warps ? vtln_warps[u] : 1.0f;
-      uint32_t key;
-      std::memcpy(&key, &w, 4);
-      auto it = index.find(key);
-      if (it == index.end()) {
-        const std::vector<int32_t> *blob;
-        int rc = get_mel_blob(plan, w, &blob);
-        if (rc != SNB_OK) return fail(rc);
-        it = index.emplace(key, static_cast<int32_t>(index.size())).first;
-        blobs.insert(blobs.end(), blob->begin(), blob->end());
-      }
-      utt_mel[u] = it->second;
-    }
-    b->nblobs = static_cast<int32_t>(index.size());
-    if (nutts == 0) {
-      const std::vector<int32_t> *blob;
-      get_mel_blob(plan, 1.0f, &blob);
-      blobs = *blob;
-      b->nblobs = 1;
-    }
-    e = cudaMalloc(&b->d_mel_blobs, blobs.size() * sizeof(int32_t));
-    if (e == cudaSuccess)
-      e = upload(b->d_mel_blobs, blobs.data(), blobs.size() * sizeof(int32_t));
-    if (e != cudaSuccess)
-      return fail(set_error(SNB_ERR_CUDA, "mel upload failed: %s", cudaGetErrorString(e)));
-  }
-  // ---- tile table (fast path) or per-utterance mel index (generic) ----
-  if (plan->fast_path) {
-    std::vector<TileDesc> tiles;
-    const int T = plan->tile_frames;
-    for (int64_t u = 0; u < nutts; ++u) {
-      const int64_t nf = b->frame_offsets[u + 1] - b->frame_offsets[u];
-      for (int64_t f0 = 0; f0 < nf; f0 += T) {
-        TileDesc td;
-        td.utt = static_cast<int32_t>(u);
-        td.f0 = static_cast<int32_t>(f0);
-        td.nf = static_cast<int32_t>(std::min<int64_t>(T, nf - f0));
-        td.mel_idx = utt_mel[u];
-        tiles.push_back(td);
-      }
-    }
-    b->ntiles = static_cast<int64_t>(tiles.size());
-    if (b->ntiles > 0) {
-      e = cudaMalloc(&b->d_tiles, tiles.size() * sizeof(TileDesc));
-      if (e == cudaSuccess)
-        e = upload(b->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc));
-      if (e != cudaSuccess)
-        return fail(set_error(SNB_ERR_CUDA, "tile upload failed: %s", cudaGetErrorString(e)));
-    }
+    o_down = add_section(b->down_offsets.data(), b->down_offsets.size() * sizeof(int64_t));
+    has_down = true;
   } else {
-    // generic kernel: per-utterance mel index, stored in the d_tiles slot
-    if (nutts > 0) {
-      e = cudaMalloc(&b->d_tiles, nutts * sizeof(int32_t));
-      if (e == cudaSuccess)
-        e = upload(b->d_tiles, utt_mel.data(), nutts * sizeof(int32_t));
-      if (e != cudaSuccess)
-        return fail(set_error(SNB_ERR_CUDA, "index upload failed: %s", cudaGetErrorString(e)));
+    // ---- mel blobs for the distinct VTLN warps of this batch ----
+    std::vector<int32_t> utt_mel(nutts, 0);
+    if (plan->has_mel) {
+      std::vector<int32_t> blobs;
+      std::map<uint32_t, int32_t> index;
+      for (int64_t u = 0; u < nutts; ++u) {
+        const float w = vtln_warps ? vtln_warps[u] : 1.0f;
+        uint32_t key;
+        std::memcpy(&key, &w, 4);
+        auto it = index.find(key);
+        if (it == index.end()) {
+          const std::vector<int32_t> *blob;
+          int rc = get_mel_blob(plan, w, &blob);
+          if (rc != SNB_OK) return fail(rc);
+          it = index.emplace(key, static_cast<int32_t>(index.size())).first;
+          blobs.insert(blobs.end(), blob->begin(), blob->end());
+        }
+        utt_mel[u] = it->second;
+      }
+      b->nblobs = static_cast<int32_t>(index.size());
+      if (nutts == 0) {
+        const std::vector<int32_t> *blob;
+        int rc = get_mel_blob(plan, 1.0f, &blob);
+        if (rc != SNB_OK) return fail(rc);
+        blobs = *blob;
+        b->nblobs = 1;
+      }
+      o_mel = add_section(blobs.data(), blobs.size() * sizeof(int32_t));
+      has_mel = true;
+    }
+    // ---- tile table (fast path) or per-utterance mel index (generic) ----
+    if (plan->fast_path) {
+      std::vector<TileDesc> tiles;
+      const int T = plan->tile_frames;
+      tiles.reserve(static_cast<size_t>(b->total_frames / T + nutts));
+      for (int64_t u = 0; u < nutts; ++u) {
+        const int64_t nf = b->frame_offsets[u + 1] - b->frame_offsets[u];
+        for (int64_t f0 = 0; f0 < nf; f0 += T) {
+          TileDesc td;
+          td.utt = static_cast<int32_t>(u);
+          td.f0 = static_cast<int32_t>(f0);
+          td.nf = static_cast<int32_t>(std::min<int64_t>(T, nf - f0));
+          td.mel_idx = utt_mel[u];
+          tiles.push_back(td);
+        }
+      }
+      b->ntiles = static_cast<int64_t>(tiles.size());
+      o_tiles = add_section(tiles.data(), tiles.size() * sizeof(TileDesc));
+      has_tiles = true;
+    } else {
+      o_tiles = add_section(utt_mel.data(), nutts * sizeof(int32_t));
+      has_tiles = true;
     }
   }
+  unsigned char *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, stage.size() + 16);
+  if (e == cudaSuccess) e = upload(d, stage.data(), stage.size());
+  if (e != cudaSuccess) {
+    if (d) cudaFree(d);
+    return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
+  }
+  b->d_blob = d;
+  b->d_sample_begin = reinterpret_cast<int64_t *>(d + o_begin);
+  b->d_sample_len = reinterpret_cast<int64_t *>(d + o_len);
+  b->d_frame_offsets = reinterpret_cast<int64_t *>(d + o_foff);
+  if (has_down) b->d_down_offsets = reinterpret_cast<int64_t *>(d + o_down);
+  if (has_mel) b->d_mel_blobs = reinterpret_cast<int32_t *>(d + o_mel);
+  if (has_tiles) b->d_tiles = reinterpret_cast<TileDesc *>(d + o_tiles);
   *out = b;
   return SNB_OK;
 }
 
 extern "C" void snb_batch_destroy(snb_batch *b) {
   if (!b) return;
-  if (b->d_sample_begin) cudaFree(b->d_sample_begin);
-  if (b->d_sample_len) cudaFree(b->d_sample_len);
-  if (b->d_frame_offsets) cudaFree(b->d_frame_offsets);
-  if (b->d_tiles) cudaFree(b->d_tiles);
-  if (b->d_mel_blobs) cudaFree(b->d_mel_blobs);
-  if (b->d_down_offsets) cudaFree(b->d_down_offsets);
+  if (b->d_blob) cudaFree(b->d_blob);
   delete b;
 }
 extern "C" int64_t snb_batch_num_utts(const snb_batch *b) { return b->nutts; }

@@ -240,11 +240,7 @@ int pitch_batch_init(const snb_plan *plan, snb_batch *b) {
   }
   info[4 * b->nutts] = off;
   b->total_down = off;
-  b->down_offsets = info;
-  cudaError_t e = cudaMalloc(&b->d_down_offsets, info.size() * sizeof(int64_t));
-  if (e == cudaSuccess)
-    e = upload(b->d_down_offsets, info.data(), info.size() * sizeof(int64_t));
-  if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch batch upload failed: %s", cudaGetErrorString(e));
+  b->down_offsets = info;       // uploaded by snb_batch_create with the other tables
   return SNB_OK;
 }
 

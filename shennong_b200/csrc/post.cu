@@ -95,9 +95,11 @@ constexpr int kMaxHalo = 16;
 
 __global__ void __launch_bounds__(256) delta_tiled_kernel(const DeltaArgs a, const int halo) {
   extern __shared__ float s_x[];                        // [nload, dim]
-  __shared__ int64_t s_first[kTileRows + 2 * kMaxHalo], s_last[kTileRows + 2 * kMaxHalo];
+  __shared__ int s_lo[kTileRows + 2 * kMaxHalo], s_hi[kTileRows + 2 * kMaxHalo];   // clamp bounds (tile rows)
   __shared__ int32_t s_group[kTileRows + 2 * kMaxHalo];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float s_taps[kMaxTaps];
+  __shared__ int s_col[1024];                           // column -> (order << 16) | d  (odim <= 1024)
+  const int tid = threadIdx.x;
   const int dim = a.dim, odim = a.dim * (a.order + 1);
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kTileRows;
   const int64_t lo = row0 - halo;
@@ -105,48 +107,59 @@ __global__ void __launch_bounds__(256) delta_tiled_kernel(const DeltaArgs a, con
   const int nrows = static_cast<int>(min(static_cast<int64_t>(kTileRows), a.total_frames - row0));
   for (int i = tid; i < nload; i += 256) {
     const int64_t t = lo + i;
+    int rlo = 0, rhi = -1, g = 0;
     if (t >= 0 && t < a.total_frames) {
       const int64_t u = find_utt_row(a.frame_offsets, a.nutts, t);
-      s_first[i] = a.frame_offsets[u];
-      s_last[i] = a.frame_offsets[u + 1] - 1;
-      s_group[i] = a.utt_group ? a.utt_group[u] : static_cast<int32_t>(u);
-    } else {
-      s_first[i] = 0; s_last[i] = -1; s_group[i] = 0;
+      const int64_t first = a.frame_offsets[u], last = a.frame_offsets[u + 1] - 1;
+      rlo = static_cast<int>(max(first - lo, static_cast<int64_t>(0)));
+      rhi = static_cast<int>(min(last - lo, static_cast<int64_t>(nload - 1)));
+      g = a.utt_group ? a.utt_group[u] : static_cast<int32_t>(u);
     }
+    s_lo[i] = rlo; s_hi[i] = rhi; s_group[i] = g;
   }
+  const int ntaps = a.tap_off[a.order] + 2 * a.tap_half[a.order] + 1;
+  for (int i = tid; i < ntaps; i += 256) s_taps[i] = a.taps[i];
+  for (int c = tid; c < odim; c += 256) s_col[c] = ((c / dim) << 16) | (c % dim);
   __syncthreads();
+  // ---- stage the normalised rows (flat, coalesced) ----
   const bool do_norm = a.norm != nullptr;
-  for (int i = warp; i < nload; i += 8) {
-    const int64_t t = lo + i;
-    const bool ok = s_last[i] >= s_first[i];
-    const float *n = do_norm ? a.norm + static_cast<int64_t>(s_group[i]) * 2 * dim : nullptr;
-    for (int d = lane; d < dim; d += 32) {
+  {
+    int i = tid / dim, d = tid - i * dim;
+    const int step_i = 256 / dim, step_d = 256 - step_i * dim;
+    for (int e = tid; e < nload * dim; e += 256) {
       float x = 0.0f;
-      if (ok) {
-        x = a.in[t * a.ld_in + d];
-        if (do_norm) x = __fadd_rn(__fmul_rn(x, n[dim + d]), n[d]);
+      if (s_hi[i] >= s_lo[i]) {
+        x = a.in[(lo + i) * a.ld_in + d];
+        if (do_norm) {
+          const float *n = a.norm + static_cast<int64_t>(s_group[i]) * 2 * dim;
+          x = __fadd_rn(__fmul_rn(x, n[dim + d]), n[d]);
+        }
       }
-      s_x[i * dim + d] = x;
+      s_x[e] = x;
+      i += step_i; d += step_d;
+      if (d >= dim) { d -= dim; ++i; }
     }
   }
   __syncthreads();
-  for (int r = warp; r < nrows; r += 8) {
-    const int64_t t = row0 + r, first = s_first[r + halo], last = s_last[r + halo];
-    float *o = a.out + t * a.ld_out;
-    for (int c = lane; c < odim; c += 32) {
-      int ord = 0, d = c;
-      while (d >= dim) { d -= dim; ++ord; }
+  // ---- outputs: one element per thread, rows contiguous => coalesced ----
+  {
+    int r = tid / odim, c = tid - r * odim;
+    const int step_r = 256 / odim, step_c = 256 - step_r * odim;
+    for (int e = tid; e < nrows * odim; e += 256) {
+      const int info = s_col[c], ord = info >> 16, d = info & 0xffff;
+      const int i0 = r + halo, clo = s_lo[i0], chi = s_hi[i0];
       const int half = a.tap_half[ord];
-      const float *taps = a.taps + a.tap_off[ord];
+      const float *taps = s_taps + a.tap_off[ord] + half;
       float acc = 0.0f;
       for (int j = -half; j <= half; ++j) {
-        const float s = taps[j + half];
-        if (s == 0.0f) continue;
-        int64_t tt = t + j;
-        tt = tt < first ? first : (tt > last ? last : tt);
-        acc = fmaf(s, s_x[static_cast<int>(tt - lo) * dim + d], acc);
+        const float sc = taps[j];
+        if (sc == 0.0f) continue;
+        const int ii = min(max(i0 + j, clo), chi);
+        acc = fmaf(sc, s_x[ii * dim + d], acc);
       }
-      o[c] = acc;
+      a.out[(row0 + r) * a.ld_out + c] = acc;
+      r += step_r; c += step_c;
+      if (c >= odim) { c -= odim; ++r; }
     }
   }
 }
@@ -388,7 +401,7 @@ extern "C" int snb_cmvn_apply_deltas(const float *d_in, int64_t ld_in, int32_t d
   a.out = d_out; a.ld_out = ld_out;
   const int halo = a.tap_half[a.order];
   const size_t smem = static_cast<size_t>(kTileRows + 2 * halo) * dim * sizeof(float);
-  if (halo <= kMaxHalo && smem <= 96 * 1024) {
+  if (halo <= kMaxHalo && smem <= 96 * 1024 && dim * (order + 1) <= 1024) {
     static std::atomic<size_t> cur{48 * 1024};
     size_t c = cur.load();
     while (smem > c) {

@@ -138,6 +138,7 @@ struct snb_batch {
   const snb_plan *plan;
   int64_t nutts = 0, total_frames = 0, total_samples = 0;
   std::vector<int64_t> sample_begin, sample_len, frame_offsets;
+  void *d_blob = nullptr;            // single device allocation; the pointers below alias it
   int64_t *d_sample_begin = nullptr, *d_sample_len = nullptr, *d_frame_offsets = nullptr;
   snb::TileDesc *d_tiles = nullptr;
   int64_t ntiles = 0;
