@@ -86,40 +86,52 @@ __global__ void __launch_bounds__(256) delta_kernel(const DeltaArgs a) {
   }
 }
 
-// Tiled variant (halo <= 16 rows): a CTA stages kTileRows + 2*halo NORMALISED
-// rows in shared memory with coalesced loads (each input element is read once
-// from global memory and normalised once), then every warp writes whole output
-// rows (coalesced) from shared-memory taps.
+// Tiled variant (ORDER <= 3, halo <= 16 rows): a CTA stages kTileRows + 2*halo
+// NORMALISED rows in shared memory with coalesced loads (each input element is
+// read once from global memory and normalised once); one thread then owns one
+// (row, dimension) pair: it reads the 2*halo+1 neighbours once from shared
+// memory and accumulates all ORDER+1 outputs in registers.
 constexpr int kTileRows = 64;
 constexpr int kMaxHalo = 16;
 
+template <int ORDER>
 __global__ void __launch_bounds__(256) delta_tiled_kernel(const DeltaArgs a, const int halo) {
   extern __shared__ float s_x[];                        // [nload, dim]
   __shared__ int s_lo[kTileRows + 2 * kMaxHalo], s_hi[kTileRows + 2 * kMaxHalo];   // clamp bounds (tile rows)
   __shared__ int32_t s_group[kTileRows + 2 * kMaxHalo];
   __shared__ float s_taps[kMaxTaps];
-  __shared__ int s_col[1024];                           // column -> (order << 16) | d  (odim <= 1024)
   const int tid = threadIdx.x;
-  const int dim = a.dim, odim = a.dim * (a.order + 1);
+  const int dim = a.dim;
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kTileRows;
   const int64_t lo = row0 - halo;
   const int nload = kTileRows + 2 * halo;
   const int nrows = static_cast<int>(min(static_cast<int64_t>(kTileRows), a.total_frames - row0));
+  // one binary search per tile (thread 0); rows of the same utterance reuse
+  // it, the few rows beyond its end search on their own (in parallel)
+  __shared__ int64_t s_u0[3];
+  if (tid == 0) {
+    const int64_t t = lo < 0 ? 0 : lo;
+    const int64_t u = find_utt_row(a.frame_offsets, a.nutts, t);
+    s_u0[0] = u; s_u0[1] = a.frame_offsets[u]; s_u0[2] = a.frame_offsets[u + 1];
+  }
+  __syncthreads();
   for (int i = tid; i < nload; i += 256) {
-    const int64_t t = lo + i;
+    const int64_t row = lo + i;
     int rlo = 0, rhi = -1, g = 0;
-    if (t >= 0 && t < a.total_frames) {
-      const int64_t u = find_utt_row(a.frame_offsets, a.nutts, t);
-      const int64_t first = a.frame_offsets[u], last = a.frame_offsets[u + 1] - 1;
+    if (row >= 0 && row < a.total_frames) {
+      int64_t u = s_u0[0], first = s_u0[1], next = s_u0[2];
+      if (row >= next) {
+        u = find_utt_row(a.frame_offsets, a.nutts, row);
+        first = a.frame_offsets[u]; next = a.frame_offsets[u + 1];
+      }
       rlo = static_cast<int>(max(first - lo, static_cast<int64_t>(0)));
-      rhi = static_cast<int>(min(last - lo, static_cast<int64_t>(nload - 1)));
+      rhi = static_cast<int>(min(next - 1 - lo, static_cast<int64_t>(nload - 1)));
       g = a.utt_group ? a.utt_group[u] : static_cast<int32_t>(u);
     }
     s_lo[i] = rlo; s_hi[i] = rhi; s_group[i] = g;
   }
-  const int ntaps = a.tap_off[a.order] + 2 * a.tap_half[a.order] + 1;
+  const int ntaps = a.tap_off[ORDER] + 2 * a.tap_half[ORDER] + 1;
   for (int i = tid; i < ntaps; i += 256) s_taps[i] = a.taps[i];
-  for (int c = tid; c < odim; c += 256) s_col[c] = ((c / dim) << 16) | (c % dim);
   __syncthreads();
   // ---- stage the normalised rows (flat, coalesced) ----
   const bool do_norm = a.norm != nullptr;
@@ -141,25 +153,29 @@ __global__ void __launch_bounds__(256) delta_tiled_kernel(const DeltaArgs a, con
     }
   }
   __syncthreads();
-  // ---- outputs: one element per thread, rows contiguous => coalesced ----
+  // ---- one thread per (row, d): all orders from one pass over the halo ----
   {
-    int r = tid / odim, c = tid - r * odim;
-    const int step_r = 256 / odim, step_c = 256 - step_r * odim;
-    for (int e = tid; e < nrows * odim; e += 256) {
-      const int info = s_col[c], ord = info >> 16, d = info & 0xffff;
+    int r = tid / dim, d = tid - r * dim;
+    const int step_r = 256 / dim, step_d = 256 - step_r * dim;
+    for (int e = tid; e < nrows * dim; e += 256) {
       const int i0 = r + halo, clo = s_lo[i0], chi = s_hi[i0];
-      const int half = a.tap_half[ord];
-      const float *taps = s_taps + a.tap_off[ord] + half;
-      float acc = 0.0f;
-      for (int j = -half; j <= half; ++j) {
-        const float sc = taps[j];
-        if (sc == 0.0f) continue;
+      float acc[ORDER + 1];
+#pragma unroll
+      for (int o = 0; o <= ORDER; ++o) acc[o] = 0.0f;
+      for (int j = -halo; j <= halo; ++j) {
         const int ii = min(max(i0 + j, clo), chi);
-        acc = fmaf(sc, s_x[ii * dim + d], acc);
+        const float x = s_x[ii * dim + d];
+#pragma unroll
+        for (int o = 0; o <= ORDER; ++o) {
+          const int half = a.tap_half[o];
+          if (j >= -half && j <= half) acc[o] = fmaf(s_taps[a.tap_off[o] + half + j], x, acc[o]);
+        }
       }
-      a.out[(row0 + r) * a.ld_out + c] = acc;
-      r += step_r; c += step_c;
-      if (c >= odim) { c -= odim; ++r; }
+      float *o_row = a.out + (row0 + r) * a.ld_out + d;
+#pragma unroll
+      for (int o = 0; o <= ORDER; ++o) o_row[o * dim] = acc[o];
+      r += step_r; d += step_d;
+      if (d >= dim) { d -= dim; ++r; }
     }
   }
 }
@@ -401,19 +417,31 @@ extern "C" int snb_cmvn_apply_deltas(const float *d_in, int64_t ld_in, int32_t d
   a.out = d_out; a.ld_out = ld_out;
   const int halo = a.tap_half[a.order];
   const size_t smem = static_cast<size_t>(kTileRows + 2 * halo) * dim * sizeof(float);
-  if (halo <= kMaxHalo && smem <= 96 * 1024 && dim * (order + 1) <= 1024) {
-    static std::atomic<size_t> cur{48 * 1024};
-    size_t c = cur.load();
-    while (smem > c) {
-      cudaError_t e = cudaFuncSetAttribute(delta_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
-      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "delta smem: %s", cudaGetErrorString(e));
-      if (cur.compare_exchange_weak(c, smem)) break;
-    }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (order <= 3 && halo <= kMaxHalo && smem <= 96 * 1024 && dim <= 256) {
     const unsigned ctas = static_cast<unsigned>((total_frames + kTileRows - 1) / kTileRows);
-    delta_tiled_kernel<<<ctas, 256, smem, static_cast<cudaStream_t>(stream)>>>(a, halo);
+    static std::atomic<size_t> cur[4] = {{48 * 1024}, {48 * 1024}, {48 * 1024}, {48 * 1024}};
+    auto launch = [&](auto kernel, std::atomic<size_t> *state) -> int {
+      size_t c = state->load();
+      while (smem > c) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "delta smem: %s", cudaGetErrorString(e));
+        if (state->compare_exchange_weak(c, smem)) break;
+      }
+      kernel<<<ctas, 256, smem, st>>>(a, halo);
+      return SNB_OK;
+    };
+    int rc2 = SNB_OK;
+    switch (order) {
+      case 0: rc2 = launch(delta_tiled_kernel<0>, &cur[0]); break;
+      case 1: rc2 = launch(delta_tiled_kernel<1>, &cur[1]); break;
+      case 2: rc2 = launch(delta_tiled_kernel<2>, &cur[2]); break;
+      default: rc2 = launch(delta_tiled_kernel<3>, &cur[3]); break;
+    }
+    if (rc2 != SNB_OK) return rc2;
   } else {
-    delta_kernel<<<row_ctas(total_frames), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    delta_kernel<<<row_ctas(total_frames), 256, 0, st>>>(a);
   }
   SNB_LAUNCH_CHECK();
   return SNB_OK;

@@ -175,7 +175,6 @@ class FusedPipeline:
         if out_host is None:
             out_host = torch.empty((total, self.out_dim), dtype=torch.float32,
                                    pin_memory=True)
-        s_in, s_c, s_out = (torch.cuda.Stream() for _ in range(3))
         chunks = [(b, min(b + chunk_utts, nutts))
                   for b in range(0, nutts, chunk_utts)]
         span = max(int(starts[e - 1] + lengths[e - 1] - starts[b]) + 64
@@ -183,11 +182,25 @@ class FusedPipeline:
         span = (span + 7) // 8 * 8
         max_rows = max(int(foffs[e] - foffs[b]) for b, e in chunks)
         nslots = 3
-        pcm_slots = [torch.empty(span, dtype=torch.int16, device='cuda')
-                     for _ in range(nslots)]
-        out_slots = [torch.empty((max_rows, self.out_dim),
-                                 dtype=torch.float32, device='cuda')
-                     for _ in range(nslots)]
+        # streams and slot buffers persist across calls: PyTorch's caching
+        # allocator pools are per stream, fresh streams would re-cudaMalloc
+        # (and later cudaFree, a device-wide sync) every buffer on every call
+        state = getattr(self, '_host_state', None)
+        if (state is None or state['span'] < span
+                or state['rows'] < max_rows):
+            state = {
+                'streams': tuple(torch.cuda.Stream() for _ in range(3)),
+                'span': span, 'rows': max_rows,
+                'pcm': [torch.empty(span, dtype=torch.int16, device='cuda')
+                        for _ in range(nslots)],
+                'out': [torch.empty((max_rows, self.out_dim),
+                                    dtype=torch.float32, device='cuda')
+                        for _ in range(nslots)]}
+            self._host_state = state
+        s_in, s_c, s_out = state['streams']
+        pcm_slots, out_slots = state['pcm'], state['out']
+        for s in (s_in, s_c, s_out):      # order after the caller's stream
+            s.wait_stream(torch.cuda.current_stream())
         free_ev = [None] * nslots        # D2H of the slot's previous use
         keep = []
         for i, (b, e) in enumerate(chunks):
