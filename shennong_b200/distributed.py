@@ -142,7 +142,6 @@ def extract_sharded(pipe, signals, speakers=None, gather=True):
     from shennong_b200 import _lib, engine
     rank, size = world()
     fo = pipe.processor._frame_opts()
-    L = _lib.lib()
     lengths = np.array([len(s) if s is not None else 0 for s in signals])
     if size > 1:
         # lengths of non-owned utterances may be unknown locally: agree on them
@@ -153,8 +152,7 @@ def extract_sharded(pipe, signals, speakers=None, gather=True):
             t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         lengths = t.cpu().numpy()
-    frames = np.array([L.snb_num_frames(int(n), _lib.ref(fo))
-                       for n in lengths], dtype=np.int64)
+    frames = engine.num_frames_array(fo, lengths).astype(np.int64)
     groups = speakers if pipe.cmvn == 'speaker' else None
     shards = shard_utterances(frames, size, groups)
     mine = shards[rank]

@@ -365,6 +365,21 @@ def process_pitch(post_opts, raw, layout, seed=0, out=None):
 # --------------------------------------------------------------------------
 # helpers for the host API
 # --------------------------------------------------------------------------
+def num_frames_array(frame_opts, lengths):
+    """Vectorised snb_num_frames (NumFrames with flush, frames.py:137) for an
+    int64 array of utterance lengths"""
+    L = _lib.lib()
+    lengths = np.asarray(lengths, dtype=np.int64)
+    size = int(L.snb_window_size(_lib.ref(frame_opts)))
+    shift = int(L.snb_window_shift(_lib.ref(frame_opts)))
+    if shift <= 0 or size <= 0:
+        raise ValueError('cannot compute nframes: sample rate too low')
+    if frame_opts.snip_edges:
+        return np.where(lengths < size, 0, 1 + (lengths - size) // shift)
+    return (lengths + shift // 2) // shift
+
+
+
 _seed_lock = threading.Lock()
 _seed_state = np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0]
 

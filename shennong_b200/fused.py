@@ -165,12 +165,9 @@ class FusedPipeline:
             raise NotImplementedError('run_host supports per-utterance cmvn')
         plans = self._plans()
         nutts = len(lengths)
-        L = engine._lib.lib()
-        fo = self.processor._frame_opts()
-        nframes = np.array(
-            [L.snb_num_frames(int(n), engine._lib.ref(fo)) for n in lengths],
-            dtype=np.int64)
-        foffs = np.concatenate(([0], np.cumsum(nframes)))
+        nframes = engine.num_frames_array(
+            self.processor._frame_opts(), lengths)
+        foffs = np.concatenate(([0], np.cumsum(nframes))).astype(np.int64)
         total = int(foffs[-1])
         if out_host is None:
             out_host = torch.empty((total, self.out_dim), dtype=torch.float32,

@@ -49,6 +49,11 @@ def test_framing_matches_oracle(kw):
     for n in [0, 1, 399, 400, 401, 559, 560, 22713, 160000, 1234567]:
         assert (L.snb_num_frames(n, _lib.ref(mine))
                 == O.orc_num_frames(n, ctypes.byref(fo)))
+    from shennong_b200 import engine
+    ns = np.array([0, 1, 399, 400, 401, 559, 560, 22713, 160000, 1234567])
+    assert np.array_equal(
+        engine.num_frames_array(mine, ns),
+        [L.snb_num_frames(int(n), _lib.ref(mine)) for n in ns])
     for f in [0, 1, 7, 139]:
         assert (L.snb_first_sample_of_frame(f, _lib.ref(mine))
                 == O.orc_first_sample_of_frame(f, ctypes.byref(fo)))
