@@ -384,8 +384,22 @@ fused_features_512_kernel(const FastArgs a) {
       // n1 < nfull: every lane holds two valid samples; n1 == nfull: the
       // ragged tail (W % 32 samples); beyond: zero padding up to 512
       float lsum = 0.0f;
-      uint32_t dither_base = 0;
-      if (dither != 0.0f) dither_base = frame_noise_key(a.seed, static_cast<uint64_t>(row0 + fidx));
+      __syncwarp();                 // the previous pass is done with this group's buffer
+      float2 *s_noise = reinterpret_cast<float2 *>(s_grp);   // [256] (dither * N(0,1)) pairs
+      if (dither != 0.0f) {
+        // rolled on purpose: ONE copy of the hash + Box-Muller code (the fully
+        // unrolled form put ~11 KB of straight-line SASS in the hot path and
+        // made the pass overflow the 32 KB instruction cache); every lane reads
+        // back only what it wrote, so no synchronisation is needed
+        const uint32_t key = frame_noise_key(a.seed, static_cast<uint64_t>(row0 + fidx));
+        const int npair = (W + 1) / 2;
+#pragma unroll 1
+        for (int pidx = hl; pidx < npair; pidx += 16) {
+          float g0, g1;
+          gauss_pair_fast(key, pidx, &g0, &g1);
+          s_noise[pidx] = make_float2(dither * g0, dither * g1);
+        }
+      }
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const int i0 = 2 * (16 * n1 + hl);
@@ -400,19 +414,16 @@ fused_features_512_kernel(const FastArgs a) {
             v1 = static_cast<float>(fr[i0 + 1]);
           }
           if (dither != 0.0f) {
-            float g0, g1;
-            gauss_pair_fast(dither_base, 16 * n1 + hl, &g0, &g1);
-            v0 = fmaf(dither, g0, v0);
-            v1 = fmaf(dither, g1, v1);
+            const float2 nz = s_noise[16 * n1 + hl];
+            v0 += nz.x; v1 += nz.y;
           }
         } else if (n1 == nfull) {
           if (i0 < W) v0 = static_cast<float>(fr[i0]);
           if (i0 + 1 < W) v1 = static_cast<float>(fr[i0 + 1]);
-          if (dither != 0.0f) {
-            float g0, g1;
-            gauss_pair_fast(dither_base, 16 * n1 + hl, &g0, &g1);
-            if (i0 < W) v0 = fmaf(dither, g0, v0);
-            if (i0 + 1 < W) v1 = fmaf(dither, g1, v1);
+          if (dither != 0.0f && i0 < W) {
+            const float2 nz = s_noise[16 * n1 + hl];
+            v0 += nz.x;
+            if (i0 + 1 < W) v1 += nz.y;
           }
         }
         xr[n1] = v0; xi[n1] = v1;
@@ -479,24 +490,29 @@ fused_features_512_kernel(const FastArgs a) {
       }
 
       // ---- 256-point complex FFT = 16 x 16 ----
-      fft16(xr, xi);                                  // over n1; lane = n2
+      // (a 2-trip loop that is NOT unrolled: one copy of the radix-16 code)
+#pragma unroll 1
+      for (int fft_pass = 0; fft_pass < 2; ++fft_pass) {
+        fft16(xr, xi);                  // pass 0: over n1 (lane = n2); pass 1: over n2 -> Z[hl + 16 k2]
+        if (fft_pass == 0) {
 #pragma unroll
-      for (int k1 = 1; k1 < 16; ++k1) {
-        const float2 w = s_tw1[k1 * 16 + hl];
-        const float r = xr[k1], i = xi[k1];
-        xr[k1] = r * w.x - i * w.y;
-        xi[k1] = r * w.y + i * w.x;
+          for (int k1 = 1; k1 < 16; ++k1) {
+            const float2 w = s_tw1[k1 * 16 + hl];
+            const float r = xr[k1], i = xi[k1];
+            xr[k1] = r * w.x - i * w.y;
+            xi[k1] = r * w.y + i * w.x;
+          }
+          __syncwarp();                 // every lane is done reading its noise
+#pragma unroll
+          for (int k1 = 0; k1 < 16; ++k1) s_x[k1 * kXStride + hl] = make_float2(xr[k1], xi[k1]);
+          __syncwarp();
+#pragma unroll
+          for (int n2 = 0; n2 < 16; ++n2) {
+            const float2 v = s_x[hl * kXStride + n2];
+            xr[n2] = v.x; xi[n2] = v.y;
+          }
+        }
       }
-      __syncwarp();                                   // previous P readers done
-#pragma unroll
-      for (int k1 = 0; k1 < 16; ++k1) s_x[k1 * kXStride + hl] = make_float2(xr[k1], xi[k1]);
-      __syncwarp();
-#pragma unroll
-      for (int n2 = 0; n2 < 16; ++n2) {
-        const float2 v = s_x[hl * kXStride + n2];
-        xr[n2] = v.x; xi[n2] = v.y;
-      }
-      fft16(xr, xi);                                  // over n2; Z[hl + 16 k2]
       __syncwarp();                                   // transpose buffer free -> reuse as P
       float *P = s_grp;
       // ---- real-FFT unpack: pairs (k, 256-k), k = hl + 16 k2, k2 < 8 ----
