@@ -237,7 +237,9 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl')
+        os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
+        dist.init_process_group(
+            'nccl', device_id=torch.device('cuda', local_rank))
     from shennong_b200 import _lib, engine
     from shennong_b200.fused import FusedPipeline
     from shennong_b200.postprocessor import DeltaPostProcessor
