@@ -187,6 +187,18 @@ int snb_compute_features(const snb_plan *plan, const snb_batch *batch,
                          const int16_t *d_pcm, int64_t pcm_capacity,
                          uint64_t seed, void *d_out, int64_t ld_out,
                          void *stream);
+/* RASTA-PLP (shennong/processor/plp.py:64-146, 582-585) needs a DEVICE scratch
+ * for the mel energies the frame-recursive filter runs on: this many bytes
+ * (0 for every other plan) ... */
+int64_t snb_feature_workspace_bytes(const snb_plan *plan,
+                                    const snb_batch *batch);
+/* ... handed to this variant of snb_compute_features (d_workspace may be NULL
+ * when snb_feature_workspace_bytes() is 0) */
+int snb_compute_features_ws(const snb_plan *plan, const snb_batch *batch,
+                            const int16_t *d_pcm, int64_t pcm_capacity,
+                            uint64_t seed, void *d_out, int64_t ld_out,
+                            void *d_workspace, int64_t workspace_bytes,
+                            void *stream);
 /* same for float32 PCM (only the energy kind: shennong's EnergyProcessor does
  * NOT cast the signal to int16, energy.py:158) */
 int snb_compute_features_f32(const snb_plan *plan, const snb_batch *batch,

@@ -111,6 +111,9 @@ SIGNATURES = {
     'snb_batch_frame_offsets_device': (vp, [vp]),
     'snb_compute_features': (ctypes.c_int, [vp, vp, vp, i64, u64, vp, i64,
                                             vp]),
+    'snb_feature_workspace_bytes': (i64, [vp, vp]),
+    'snb_compute_features_ws': (ctypes.c_int, [vp, vp, vp, i64, u64, vp, i64,
+                                               vp, i64, vp]),
     'snb_compute_features_f32': (ctypes.c_int, [vp, vp, vp, i64, u64, vp, i64,
                                                 vp]),
     'snb_compute_deltas': (ctypes.c_int, [vp, i64, i32, vp, i64, i64, i32,

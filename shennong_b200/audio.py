@@ -187,7 +187,8 @@ class Audio:
             raise ValueError(f'unsupported audio data type: {dtype}')
         is_float = target.kind == 'f'
         if self.dtype == np.int16:
-            data = self.data / 2**15 if is_float else self.data * 2**15
+            data = (self.data / 2**15 if is_float
+                    else self.data.astype(np.int32) * 2**15)
         elif self.dtype == np.int32:
             data = self.data / 2**30 if is_float else self.data / 2**15
         else:

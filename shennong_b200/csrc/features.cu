@@ -68,6 +68,75 @@ struct TailTables {       // tables the tails read (shared memory in both paths)
   MelView mel;
 };
 
+// PLP after the (loudness-weighted, compressed) mel energies are in
+// mel[1..B] = scratch[1..B] (plp.py:590-626): duplicate the ends, IDFT to the
+// autocorrelation, lane-parallel Levinson-Durbin and LPC -> cepstrum, lifter,
+// scale, energy, HTK reorder.
+template <int G>
+__device__ __forceinline__ void plp_finish(const FeatParams &p, const TailTables &t, float *scratch,
+                                           float log_energy, float *out_row, bool valid, int gl) {
+  const snb_feat_opts &xo = p.xo;
+  const int B = p.B, nc = xo.num_ceps;
+  float *mel = scratch;
+  // ---- PLP tail (plp.py:590-626) ----
+  const int L = xo.lpc_order;       // <= G - 1 (checked at plan creation)
+  if (gl == 0) { mel[0] = mel[1]; mel[B + 1] = mel[B]; }
+  __syncwarp();
+  float *ac = scratch + (B + 2);    // [L+1] (useg/dseg follow at B+2 + L+2)
+  for (int i = gl; i <= L; i += G) {
+    const float *row = t.idft + i * (B + 2);
+    float acc = 0.0f;
+    for (int j = 0; j < B + 2; ++j) acc = fmaf(row[j], mel[j], acc);
+    ac[i] = acc;
+  }
+  __syncwarp();
+  // Levinson-Durbin, lanes parallel over the coefficient index j
+  const int gbase = (threadIdx.x & 31) & ~(G - 1);  // first lane of my group
+  float E = ac[0];
+  float lpc = 0.0f;                 // lane j holds lpc[j]
+  for (int i = 0; i < L; ++i) {
+    // ki = (ac[i+1] + sum_{j<i} lpc[j] * ac[i-j]) / E
+    float part = (gl < i) ? lpc * ac[i - gl] : 0.0f;
+    part = group_sum<G>(part);
+    float ki = (ac[i + 1] + part) / E;
+    float c = 1.0f - ki * ki;
+    if (c < 1.0e-5f) c = 1.0e-5f;
+    E *= c;
+    // lpc'[j] = lpc[j] - ki * lpc[i-j-1] (j<i); lpc'[i] = -ki
+    const int src = (i - gl - 1) & (G - 1);
+    const float other = __shfl_sync(SNB_FULL_MASK, lpc, gbase + src);
+    if (gl < i) lpc = lpc - ki * other;
+    else if (gl == i) lpc = -ki;
+  }
+  // ComputeLpc returns -log(1/E); plp.py:603 floors with float64 eps
+  float residual = -logf(1.0f / E);
+  residual = fmaxf(residual, 2.220446049250313e-16f);
+  // LPC -> cepstrum (plp.py:164-168), lane i holds cep[i]
+  float cep = 0.0f;
+  for (int i = 0; i < L; ++i) {
+    // sum_{j<i} (i-j) * lpc[j] * cep[i-j-1]
+    const int src = (i - gl - 1) & (G - 1);
+    const float cj = __shfl_sync(SNB_FULL_MASK, cep, gbase + src);
+    float part = (gl < i) ? static_cast<float>(i - gl) * lpc * cj : 0.0f;
+    part = group_sum<G>(part);
+    const float mine = -lpc - part / static_cast<float>(i + 1);
+    if (gl == i) cep = mine;
+  }
+  // out[0] = residual, out[c] = cep[c-1]; lifter, scale, energy, htk reorder
+  // (nc <= L + 1 <= G: one column per lane; the shuffle is warp-uniform)
+  const float prev = __shfl_sync(SNB_FULL_MASK, cep, gbase + ((gl - 1) & (G - 1)));
+  if (gl < nc) {
+    const int c = gl;
+    float v = (c == 0) ? residual : prev;
+    if (xo.cepstral_lifter != 0.0f) v *= t.lifter[c];
+    if (xo.cepstral_scale != 1.0f) v *= xo.cepstral_scale;
+    if (c == 0 && xo.use_energy) v = log_energy;
+    int col = c;
+    if (xo.htk_compat) col = (c == 0) ? nc - 1 : c - 1;
+    if (valid) out_row[col] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // tails: from the power spectrum P[0..N/2] (shared memory, private to the
 // lane group) to one output row.  G = lanes per frame (16 or 32); all lanes of
@@ -175,63 +244,7 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
     }
     return;
   }
-  // ---- PLP tail (plp.py:590-626) ----
-  const int L = xo.lpc_order;       // <= G - 1 (checked at plan creation)
-  if (gl == 0) { mel[0] = mel[1]; mel[B + 1] = mel[B]; }
-  __syncwarp();
-  float *ac = scratch + (B + 2);    // [L+1] (useg/dseg follow at B+2 + L+2)
-  for (int i = gl; i <= L; i += G) {
-    const float *row = t.idft + i * (B + 2);
-    float acc = 0.0f;
-    for (int j = 0; j < B + 2; ++j) acc = fmaf(row[j], mel[j], acc);
-    ac[i] = acc;
-  }
-  __syncwarp();
-  // Levinson-Durbin, lanes parallel over the coefficient index j
-  const int gbase = (threadIdx.x & 31) & ~(G - 1);  // first lane of my group
-  float E = ac[0];
-  float lpc = 0.0f;                 // lane j holds lpc[j]
-  for (int i = 0; i < L; ++i) {
-    // ki = (ac[i+1] + sum_{j<i} lpc[j] * ac[i-j]) / E
-    float part = (gl < i) ? lpc * ac[i - gl] : 0.0f;
-    part = group_sum<G>(part);
-    float ki = (ac[i + 1] + part) / E;
-    float c = 1.0f - ki * ki;
-    if (c < 1.0e-5f) c = 1.0e-5f;
-    E *= c;
-    // lpc'[j] = lpc[j] - ki * lpc[i-j-1] (j<i); lpc'[i] = -ki
-    const int src = (i - gl - 1) & (G - 1);
-    const float other = __shfl_sync(SNB_FULL_MASK, lpc, gbase + src);
-    if (gl < i) lpc = lpc - ki * other;
-    else if (gl == i) lpc = -ki;
-  }
-  // ComputeLpc returns -log(1/E); plp.py:603 floors with float64 eps
-  float residual = -logf(1.0f / E);
-  residual = fmaxf(residual, 2.220446049250313e-16f);
-  // LPC -> cepstrum (plp.py:164-168), lane i holds cep[i]
-  float cep = 0.0f;
-  for (int i = 0; i < L; ++i) {
-    // sum_{j<i} (i-j) * lpc[j] * cep[i-j-1]
-    const int src = (i - gl - 1) & (G - 1);
-    const float cj = __shfl_sync(SNB_FULL_MASK, cep, gbase + src);
-    float part = (gl < i) ? static_cast<float>(i - gl) * lpc * cj : 0.0f;
-    part = group_sum<G>(part);
-    const float mine = -lpc - part / static_cast<float>(i + 1);
-    if (gl == i) cep = mine;
-  }
-  // out[0] = residual, out[c] = cep[c-1]; lifter, scale, energy, htk reorder
-  // (nc <= L + 1 <= G: one column per lane; the shuffle is warp-uniform)
-  const float prev = __shfl_sync(SNB_FULL_MASK, cep, gbase + ((gl - 1) & (G - 1)));
-  if (gl < nc) {
-    const int c = gl;
-    float v = (c == 0) ? residual : prev;
-    if (xo.cepstral_lifter != 0.0f) v *= t.lifter[c];
-    if (xo.cepstral_scale != 1.0f) v *= xo.cepstral_scale;
-    if (c == 0 && xo.use_energy) v = log_energy;
-    int col = c;
-    if (xo.htk_compat) col = (c == 0) ? nc - 1 : c - 1;
-    if (valid) out_row[col] = v;
-  }
+  plp_finish<G>(p, t, scratch, log_energy, out_row, valid, gl);
 }
 
 // energy kind (energy.py:171-183): float64 sum of squares of the processed
@@ -717,6 +730,89 @@ generic_features_kernel(const GenArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// RASTA-PLP (plp.py:64-146): per (utterance, mel bin), frames in order.
+// x = log(mel + FLT_EPSILON) in float32; frames 0..3 output exp(0) and prime
+// the FIR state (lfilter(num, 1, first4, zi = lfilter_zi(num, 1) * x[0]));
+// from frame 4 on y = sum b_k x_{t-k} + 0.94 y_{t-1} in float64 (direct form
+// II transposed, like scipy.signal.lfilter), output exp((float)y).  In place.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rasta_kernel(float *mel, int64_t ld, int col0, int B,
+                                                    const int64_t *frame_offsets, int64_t nutts) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= nutts * B) return;
+  const int64_t u = idx / B;
+  const int b = static_cast<int>(idx - u * B);
+  const int64_t first = frame_offsets[u], F = frame_offsets[u + 1] - first;
+  const double b0 = 0.2, b1 = 0.1, b2 = -0.0, b3 = -0.1, b4 = -0.2;
+  float *col = mel + first * ld + col0 + b;
+  double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+  for (int64_t t = 0; t < F; ++t) {
+    const float xf = logf(col[t * ld] + FLT_EPSILON);
+    const double x = static_cast<double>(xf);
+    if (t < 4) {
+      if (t == 0) {
+        // lfilter_zi(num, 1) = [b1+b2+b3+b4, b2+b3+b4, b3+b4, b4], scaled by x[0]
+        z3 = b4 * x; z2 = (b3 + b4) * x; z1 = (b2 + (b3 + b4)) * x; z0 = (b1 + (b2 + (b3 + b4))) * x;
+      }
+      z0 = b1 * x + z1; z1 = b2 * x + z2; z2 = b3 * x + z3; z3 = b4 * x;
+      col[t * ld] = expf(0.0f);
+    } else {
+      const double y = b0 * x + z0;
+      z0 = b1 * x + z1 + 0.94 * y; z1 = b2 * x + z2; z2 = b3 * x + z3; z3 = b4 * x;
+      col[t * ld] = expf(static_cast<float>(y));
+    }
+  }
+}
+
+// PLP tail from precomputed (filtered) mel energies: one warp per frame
+struct PlpMelArgs {
+  FeatParams p;
+  const float *mel;          // [F, ld_mel]: column 0 log-energy, columns 1..B mel
+  int64_t ld_mel;
+  const int64_t *frame_offsets;
+  const int32_t *utt_mel_idx;   // may be NULL (blob 0)
+  const TileDesc *tiles;        // fast-path batches carry the mel index per tile
+  const int32_t *mel_blobs;
+  int64_t nutts, total_frames;
+  float *out;
+  int64_t ld_out;
+  int tables_floats, warp_floats;
+};
+
+__global__ void __launch_bounds__(kGenWarps * 32) plp_from_mel_kernel(const PlpMelArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FeatParams &p = a.p;
+  const snb_feat_opts &xo = p.xo;
+  float *s_tables = reinterpret_cast<float *>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = p.B;
+  float *s_lifter = s_tables;
+  float *s_idft = s_lifter + xo.num_ceps;
+  for (int i = tid; i < xo.num_ceps; i += blockDim.x) s_lifter[i] = p.t.lifter[i];
+  for (int i = tid; i < (xo.lpc_order + 1) * (B + 2); i += blockDim.x) s_idft[i] = p.t.idft[i];
+  __syncthreads();
+  float *scratch = s_tables + a.tables_floats + static_cast<int64_t>(warp) * a.warp_floats;
+  TailTables tt;
+  tt.dct = nullptr; tt.lifter = s_lifter; tt.idft = s_idft;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * kGenWarps + warp; row < a.total_frames;
+       row += static_cast<int64_t>(gridDim.x) * kGenWarps) {
+    const int64_t utt = find_utt(a.frame_offsets, a.nutts, row);
+    // all the utterances of a RASTA batch share the blob unless VTLN warps differ
+    int mel_idx = 0;
+    if (a.utt_mel_idx) mel_idx = a.utt_mel_idx[utt];
+    tt.mel = mel_view(a.mel_blobs + static_cast<int64_t>(mel_idx) * p.mel_blob_stride, p);
+    const float *mrow = a.mel + row * a.ld_mel;
+    float log_energy = mrow[0];
+    if (xo.energy_floor > 0.0f && log_energy < p.log_energy_floor) log_energy = p.log_energy_floor;
+    __syncwarp();
+    for (int b = lane; b < B; b += 32)
+      scratch[1 + b] = powf(mrow[1 + b] * tt.mel.loudness[b], xo.compress_factor);
+    __syncwarp();
+    plp_finish<32>(p, tt, scratch, log_energy, a.out + row * a.ld_out, true, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host: plan
 // ---------------------------------------------------------------------------
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -885,8 +981,6 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
     case SNB_FEAT_PLP:
       if (xo->num_ceps <= 0 || xo->num_ceps > xo->lpc_order + 1)
         return fail(set_error(SNB_ERR_OPTION, "num_ceps must be in [1, lpc_order+1]"));
-      if (xo->rasta)
-        return fail(set_error(SNB_ERR_UNSUPPORTED, "rasta filtering is not implemented on the GPU path yet"));
       p.dim = xo->num_ceps;
       break;
     default:
@@ -964,7 +1058,31 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
   rc = feature_plan_finalize(plan);
   if (rc != SNB_OK) {
     cudaFree(d);
+    plan->d_tables = nullptr;
     return fail(rc);
+  }
+  if (kind == SNB_FEAT_PLP && xo->rasta) {
+    // the frame-recursive RASTA filter sits between the mel energies and the
+    // PLP tail: an internal filterbank-kind plan emits [log-energy | linear mel]
+    snb_feat_opts mx;
+    std::memset(&mx, 0, sizeof(mx));
+    mx.kind = SNB_FEAT_FBANK;
+    mx.use_energy = 1;
+    mx.raw_energy = xo->raw_energy;
+    mx.use_log_fbank = 0;
+    mx.use_power = 1;
+    snb_plan *mel_plan = nullptr;
+    rc = snb_feature_plan_create(fo, mo, &mx, &mel_plan);
+    if (rc != SNB_OK) {
+      snb_plan_destroy(plan);
+      return rc;
+    }
+    mel_plan->params.eps_energy = p.eps_energy;   // plp.py floors with float64 eps
+    if (!xo->use_energy) {
+      mel_plan->params.need_raw_energy = 0;
+      mel_plan->params.need_post_energy = 0;
+    }
+    plan->rasta_mel_plan = mel_plan;
   }
   *out = plan;
   return SNB_OK;
@@ -973,6 +1091,7 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
 extern "C" void snb_plan_destroy(snb_plan *plan) {
   if (!plan) return;
   if (plan->d_tables) cudaFree(plan->d_tables);
+  if (plan->rasta_mel_plan) snb_plan_destroy(plan->rasta_mel_plan);
   if (plan->kind == 1) pitch_plan_free(plan);
   delete plan;
 }
@@ -1146,8 +1265,8 @@ static int num_sms() {
 
 static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
                                  const float *d_wave, int64_t capacity, uint64_t seed, void *d_out,
-                                 int64_t ld_out, void *stream_) {
-  if (!plan || !batch || plan->kind != 0 || batch->plan != plan)
+                                 int64_t ld_out, void *stream_, bool foreign_batch = false) {
+  if (!plan || !batch || plan->kind != 0 || (batch->plan != plan && !foreign_batch))
     return set_error(SNB_ERR_VALUE, "plan/batch mismatch");
   if (batch->total_frames == 0) return SNB_OK;
   if ((!d_pcm && !d_wave) || !d_out) return set_error(SNB_ERR_VALUE, "null device buffer");
@@ -1224,9 +1343,69 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
   return SNB_OK;
 }
 
+extern "C" int64_t snb_feature_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
+  if (!plan || !batch || plan->kind != 0 || !plan->rasta_mel_plan) return 0;
+  return (batch->total_frames + 1) * static_cast<int64_t>(plan->params.B + 1) * 4 + 256;
+}
+
+extern "C" int snb_compute_features_ws(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
+                                       int64_t pcm_capacity, uint64_t seed, void *d_out, int64_t ld_out,
+                                       void *d_workspace, int64_t workspace_bytes, void *stream_) {
+  if (!plan || plan->kind != 0 || !plan->rasta_mel_plan)
+    return compute_features_impl(plan, batch, d_pcm, nullptr, pcm_capacity, seed, d_out, ld_out, stream_);
+  if (!batch || batch->plan != plan) return set_error(SNB_ERR_VALUE, "plan/batch mismatch");
+  if (batch->total_frames == 0) return SNB_OK;
+  if (!d_workspace || workspace_bytes < snb_feature_workspace_bytes(plan, batch))
+    return set_error(SNB_ERR_VALUE, "RASTA-PLP needs a workspace of snb_feature_workspace_bytes() bytes");
+  const FeatParams &p = plan->params;
+  if (ld_out < p.dim) return set_error(SNB_ERR_VALUE, "ld_out %lld < dim %d", (long long)ld_out, p.dim);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float *mel = static_cast<float *>(d_workspace);
+  const int64_t ld_mel = p.B + 1;
+  // 1. [log-energy | linear mel energies] with the batch of the PLP plan (same
+  //    framing, tiles and mel blobs as the internal filterbank plan)
+  int rc = compute_features_impl(plan->rasta_mel_plan, batch, d_pcm, nullptr, pcm_capacity, seed, mel,
+                                 ld_mel, stream_, /*foreign_batch=*/true);
+  if (rc != SNB_OK) return rc;
+  // 2. the frame-recursive filter, in place
+  const int64_t nthreads = batch->nutts * p.B;
+  rasta_kernel<<<static_cast<unsigned>((nthreads + 127) / 128), 128, 0, stream>>>(
+      mel, ld_mel, 1, p.B, batch->d_frame_offsets, batch->nutts);
+  SNB_LAUNCH_CHECK();
+  // 3. PLP tail from the filtered energies
+  PlpMelArgs a;
+  a.p = p;
+  a.mel = mel;
+  a.ld_mel = ld_mel;
+  a.frame_offsets = batch->d_frame_offsets;
+  a.utt_mel_idx = plan->fast_path ? nullptr : reinterpret_cast<const int32_t *>(batch->d_tiles);
+  a.tiles = plan->fast_path ? batch->d_tiles : nullptr;
+  a.mel_blobs = batch->d_mel_blobs;
+  a.nutts = batch->nutts;
+  a.total_frames = batch->total_frames;
+  a.out = static_cast<float *>(d_out);
+  a.ld_out = ld_out;
+  const snb_feat_opts &xo = p.xo;
+  a.tables_floats = align_up(xo.num_ceps + (xo.lpc_order + 1) * (p.B + 2), 4);
+  a.warp_floats = align_up(3 * (p.B + 2) + xo.lpc_order + 2 + 8, 4);
+  if (plan->fast_path && batch->nblobs > 1)
+    return set_error(SNB_ERR_UNSUPPORTED, "RASTA-PLP with several VTLN warps in one batch");
+  const size_t smem = static_cast<size_t>(a.tables_floats + kGenWarps * a.warp_floats) * 4;
+  static std::atomic<size_t> plp_smem{48 * 1024};
+  rc = ensure_smem(plp_from_mel_kernel, smem, &plp_smem);
+  if (rc != SNB_OK) return rc;
+  const int64_t want = (batch->total_frames + kGenWarps - 1) / kGenWarps;
+  const int64_t grid = std::min<int64_t>(want, static_cast<int64_t>(num_sms()) * 8);
+  plp_from_mel_kernel<<<static_cast<unsigned>(grid), kGenWarps * 32, smem, stream>>>(a);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 extern "C" int snb_compute_features(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
                                     int64_t pcm_capacity, uint64_t seed, void *d_out, int64_t ld_out,
                                     void *stream) {
+  if (plan && plan->kind == 0 && plan->rasta_mel_plan)
+    return set_error(SNB_ERR_VALUE, "RASTA-PLP plans need snb_compute_features_ws()");
   return compute_features_impl(plan, batch, d_pcm, nullptr, pcm_capacity, seed, d_out, ld_out, stream);
 }
 

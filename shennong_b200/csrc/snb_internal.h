@@ -129,6 +129,8 @@ struct snb_plan {
   // VTLN mel-blob cache (host side), keyed by warp bits
   mutable std::mutex mu;
   mutable std::map<uint32_t, std::vector<int32_t>> mel_blobs;
+  // RASTA-PLP: internal plan producing linear mel energies (+ log-energy)
+  snb_plan *rasta_mel_plan = nullptr;
   // pitch plan
   snb_pitch_opts po;
   snb::PitchTables *pitch = nullptr;

@@ -207,12 +207,19 @@ def compute_features(plan, batch, seed=0, out=None, float64=False):
         out = torch.empty((batch.total_frames, plan.dim), dtype=dtype,
                           device='cuda')
     packed = batch.packed
-    fun = (_lib.lib().snb_compute_features_f32 if packed.is_float
-           else _lib.lib().snb_compute_features)
-    _lib.check(fun(
+    L = _lib.lib()
+    seed = ctypes.c_uint64(int(seed) & (2**64 - 1))
+    if packed.is_float:
+        _lib.check(L.snb_compute_features_f32(
+            plan.handle, batch.handle, _ptr(packed.dev), packed.dev.numel(),
+            seed, _ptr(out), out.stride(0), _stream_ptr()))
+        return out
+    nbytes = int(L.snb_feature_workspace_bytes(plan.handle, batch.handle))
+    work = (torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+            if nbytes > 0 else None)      # RASTA-PLP scratch
+    _lib.check(L.snb_compute_features_ws(
         plan.handle, batch.handle, _ptr(packed.dev), packed.dev.numel(),
-        ctypes.c_uint64(int(seed) & (2**64 - 1)), _ptr(out), out.stride(0),
-        _stream_ptr()))
+        seed, _ptr(out), out.stride(0), _ptr(work), nbytes, _stream_ptr()))
     return out
 
 

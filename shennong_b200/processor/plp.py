@@ -3,8 +3,8 @@
 
 The reference runs this recipe as a per-frame PYTHON loop over pykaldi
 primitives (plp.py:510-626); here it is a tail of the fused CUDA kernel.
-RASTA filtering (plp.py:64-146) is a frame-recursive IIR that is not on the
-GPU path yet: ``rasta=True`` raises NotImplementedError at process time.
+With ``rasta=True`` the frame-recursive RASTA filter (plp.py:64-146) runs as
+its own kernel between the mel energies and the PLP tail.
 """
 
 import numpy as np

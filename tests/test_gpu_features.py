@@ -161,8 +161,26 @@ def test_invalid_options_raise_like_kaldi(audio):
     with pytest.raises(ValueError):
         stereo = Audio(np.zeros((1000, 2), np.int16), 16000)
         MfccProcessor().process(stereo)
-    with pytest.raises(NotImplementedError):
-        PlpProcessor(rasta=True).process(audio)
+
+
+@pytest.mark.parametrize('kwargs', [
+    {}, {'use_energy': False}, {'raw_energy': False, 'num_bins': 30},
+    {'frame_length': 0.05}, {'htk_compat': True, 'cepstral_lifter': 0}])
+def test_rasta_plp(pcm, kwargs):
+    """RASTA-PLP (plp.py:64-146): first 4 frames see unit mel energies, then
+    the float64 IIR; fast and generic paths"""
+    feats = run('plp', pcm, rasta=True, **kwargs)
+    ref = oracle.features('plp', pcm, rasta=True, **kwargs)
+    scale_close(feats.data, ref, tol=1e-4)
+    plain = run('plp', pcm, **kwargs)
+    assert not np.allclose(plain.data[10:, 1:], feats.data[10:, 1:], atol=1e-2)
+    # short utterances: fewer than 4 frames never leave the priming phase
+    short = synth_utterance(3, 800)
+    scale_close(run('plp', short, rasta=True).data,
+                oracle.features('plp', short, rasta=True), tol=1e-4)
+    long = synth_utterance(5, 160000)
+    scale_close(run('plp', long, rasta=True).data,
+                oracle.features('plp', long, rasta=True), tol=1e-4)
 
 
 def test_edge_lengths():
