@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(kPitchThreads) pitch_track_kernel(const TrackA
   int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + a.nstates * a.up_nw_max);
   int32_t *s_upn = s_upfirst + a.nstates;
   __shared__ double s_red[kPitchThreads / 32];
+  __shared__ int s_abp[kPitchThreads * kMaxStatesPerThread / 16 + 2];
+  __shared__ float s_acost[kPitchThreads * kMaxStatesPerThread / 16 + 2];
   __shared__ float s_fred[kPitchThreads / 32];
   __shared__ int s_ired[kPitchThreads / 32];
   __shared__ float s_scalar[4];
@@ -457,17 +459,50 @@ __global__ void __launch_bounds__(kPitchThreads) pitch_track_kernel(const TrackA
         }
       }
       // ---- exact Viterbi step: min_j pen[|i-j|] + prev[j] (first minimal j) ----
+      // The transition cost is convex in (i - j), so the minimising j is
+      // non-decreasing in i (Monge property).  Level 1: every kAnchor-th state
+      // (and the last one) scans all j, one warp per anchor.  Level 2: every
+      // other state scans only [bp(left anchor), bp(right anchor)].  ~10x fewer
+      // evaluations than the full 417 x 417 scan, same minimum.
+      constexpr int kAnchor = 16;
+      const int nanchor = (ns - 1 + kAnchor - 1) / kAnchor + 1;     // 0, 16, ..., ns-1
+      for (int t = warp; t < nanchor; t += kPitchThreads / 32) {
+        const int i = min(t * kAnchor, ns - 1);
+        float best = FLT_MAX;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < ns; j += 32) {
+          const int d = j > i ? j - i : i - j;
+          const float c = __fadd_rn(s_pen[d], s_prev[j]);
+          if (c < best) { best = c; bj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(SNB_FULL_MASK, best, o);
+          const int oj = __shfl_xor_sync(SNB_FULL_MASK, bj, o);
+          if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+        if (lane == 0) { s_abp[t] = bj; s_acost[t] = best; }
+      }
+      __syncthreads();
       float lmin = FLT_MAX;
 #pragma unroll
       for (int r = 0; r < kMaxStatesPerThread; ++r) {
         const int i = tid + r * kPitchThreads;
         if (i < ns) {
-          float best = FLT_MAX;
-          int bj = 0;
-          for (int j = 0; j < ns; ++j) {
-            const int d = j > i ? j - i : i - j;
-            const float c = __fadd_rn(s_pen[d], s_prev[j]);
-            if (c < best) { best = c; bj = j; }
+          const int ta = i / kAnchor;
+          float best;
+          int bj;
+          if (i == ta * kAnchor || i == ns - 1) {
+            const int t = (i == ns - 1) ? nanchor - 1 : ta;
+            best = s_acost[t]; bj = s_abp[t];
+          } else {
+            const int jlo = s_abp[ta], jhi = s_abp[min(ta + 1, nanchor - 1)];
+            best = FLT_MAX; bj = jlo;
+            for (int j = jlo; j <= jhi; ++j) {
+              const int d = j > i ? j - i : i - j;
+              const float c = __fadd_rn(s_pen[d], s_prev[j]);
+              if (c < best) { best = c; bj = j; }
+            }
           }
           bp[f * ns + i] = static_cast<int16_t>(bj);
           const float v = __fadd_rn(best, lc[r]);
@@ -625,14 +660,23 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
   }
 }
 
-static int pitch_grid(int64_t nutts) {
-  int dev = 0, sms = 148;
+static size_t track_smem(const PitchTables *t);
+
+// persistent CTAs: exactly what is resident at once (a larger grid would run a
+// second, underfilled wave)
+static int pitch_grid(const PitchTables *t, int64_t nutts) {
+  int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
     cudaGetLastError();
     sms = 148;
   }
-  return static_cast<int>(std::min<int64_t>(nutts, static_cast<int64_t>(sms) * 4));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pitch_track_kernel, kPitchThreads,
+                                                    track_smem(t)) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return static_cast<int>(std::min<int64_t>(nutts, static_cast<int64_t>(sms) * per_sm));
 }
 
 static size_t track_smem(const PitchTables *t) {
@@ -680,7 +724,7 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 extern "C" int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
   if (!plan || plan->kind != 1 || !batch) return -1;
   const PitchTables *t = plan->pitch;
-  const int64_t grid = pitch_grid(batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
+  const int64_t grid = pitch_grid(t, batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
   size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4);
   bytes += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
   bytes += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
@@ -699,7 +743,7 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
     return set_error(SNB_ERR_VALUE, "pitch workspace too small");
   const PitchTables *t = plan->pitch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int64_t grid = pitch_grid(batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
+  const int64_t grid = pitch_grid(t, batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
   unsigned char *ws = static_cast<unsigned char *>(d_workspace);
   float *down = reinterpret_cast<float *>(ws);
   ws += align256(static_cast<size_t>(batch->total_down + 8) * 4);
