@@ -285,7 +285,11 @@ struct FastArgs {
   int use_tma;
 };
 
-__global__ void __launch_bounds__(kFastThreads, 3)
+// kMinBlocks = 3: 80 registers; kMinBlocks = 4: 64 registers (no spills), 32
+// resident warps per SM -- selected at plan time when the shared memory of four
+// CTAs fits (SNB_FUSED_OCC=3|4 overrides)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kFastThreads, kMinBlocks)
 fused_features_512_kernel(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FeatParams &p = a.p;
@@ -842,12 +846,27 @@ int feature_plan_finalize(snb_plan *plan) {
   plan->fast_path = false;
   const int group_need = (xo.kind == SNB_FEAT_PLP) ? xo.lpc_order + 1 : 1;
   if (p.N == 512 && p.W > 256 && p.B <= 200 && group_need <= 16) {
-    // tile so that the staged span stays small (<= 24 KB of int16)
+    // tile so that the staged span stays small (<= 24 KB of int16); prefer
+    // the tile size that lets four CTAs share an SM
+    static const int forced_occ = getenv("SNB_FUSED_OCC") ? atoi(getenv("SNB_FUSED_OCC")) : 0;
     int t = 32;
     while (t > 1 && ((t - 1) * p.S + p.W + 16) * 2 > 24 * 1024) t /= 2;
     plan->tile_frames = t;
+    plan->fused_occ = 3;
     FastSmemLayout sm;
     fast_layout(plan, &sm);
+    const int budget4 = (227 * 1024) / 4 - 2048;     // per CTA, minus static + reserved
+    if (forced_occ != 3) {
+      if (sm.total <= budget4) {
+        plan->fused_occ = 4;
+      } else if (t >= 32) {
+        plan->tile_frames = 16;
+        FastSmemLayout sm16;
+        fast_layout(plan, &sm16);
+        if (sm16.total <= budget4) { plan->fused_occ = 4; sm = sm16; }
+        else plan->tile_frames = t;
+      }
+    }
     if (sm.total <= 200 * 1024) {
       plan->fast_path = true;
       plan->smem_bytes = sm.total;
@@ -1250,7 +1269,7 @@ static int ensure_smem(K kernel, size_t bytes, std::atomic<size_t> *current) {
   }
   return SNB_OK;
 }
-static std::atomic<size_t> g_fast_smem{0}, g_gen_smem{0};
+static std::atomic<size_t> g_fast_smem{0}, g_fast_smem4{0}, g_gen_smem{0};
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -1293,14 +1312,19 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
     a.seed = seed;
     static const bool no_tma = getenv("SNB_NO_TMA") != nullptr;
     a.use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(d_pcm) % 16 == 0)) ? 1 : 0;
-    int rc = ensure_smem(fused_features_512_kernel, a.sm.total, &g_fast_smem);
+    auto launch = [&](auto kernel, std::atomic<size_t> *state) -> int {
+      int rc = ensure_smem(kernel, a.sm.total, state);
+      if (rc != SNB_OK) return rc;
+      int per_sm = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFastThreads, a.sm.total);
+      if (per_sm < 1) per_sm = 1;
+      const int64_t grid = std::min<int64_t>(batch->ntiles, static_cast<int64_t>(num_sms()) * per_sm);
+      kernel<<<static_cast<unsigned>(grid), kFastThreads, a.sm.total, stream>>>(a);
+      return SNB_OK;
+    };
+    int rc = (plan->fused_occ == 4) ? launch(fused_features_512_kernel<4>, &g_fast_smem4)
+                                    : launch(fused_features_512_kernel<3>, &g_fast_smem);
     if (rc != SNB_OK) return rc;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_features_512_kernel, kFastThreads,
-                                                  a.sm.total);
-    if (per_sm < 1) per_sm = 1;
-    const int64_t grid = std::min<int64_t>(batch->ntiles, static_cast<int64_t>(num_sms()) * per_sm);
-    fused_features_512_kernel<<<static_cast<unsigned>(grid), kFastThreads, a.sm.total, stream>>>(a);
     SNB_LAUNCH_CHECK();
     return SNB_OK;
   }

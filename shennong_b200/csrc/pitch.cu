@@ -316,7 +316,7 @@ __device__ __forceinline__ double block_sum_f64(double v, double *s_red) {
   return t;
 }
 
-__global__ void __launch_bounds__(kPitchThreads) pitch_track_kernel(const TrackArgs a) {
+__global__ void __launch_bounds__(kPitchThreads, 4) pitch_track_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_win = reinterpret_cast<float *>(smem_raw);          // [full_len]
   float *s_np = s_win + a.full_len;                             // nccf_pitch [nmeas]
@@ -442,21 +442,15 @@ __global__ void __launch_bounds__(kPitchThreads) pitch_track_kernel(const TrackA
       }
       __syncthreads();
       // ---- upsample nccf_pitch to the log-spaced lags; local cost ----
-      float lc[kMaxStatesPerThread];
-#pragma unroll
-      for (int r = 0; r < kMaxStatesPerThread; ++r) {
-        const int i = tid + r * kPitchThreads;
-        lc[r] = 0.0f;
-        if (i < ns) {
-          const float *w = s_upw + i * a.up_nw_max;
-          const int first = s_upfirst[i], n = s_upn[i];
-          float acc = 0.0f;
-          for (int j = 0; j < n; ++j) acc = fmaf(w[j], s_np[first + j], acc);
-          // local_cost = 1 - nccf; += soft_min_f0 * lag * nccf
-          float c = __fadd_rn(1.0f, -acc);
-          c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
-          lc[r] = c;
-        }
+      for (int i = tid; i < ns; i += kPitchThreads) {
+        const float *w = s_upw + i * a.up_nw_max;
+        const int first = s_upfirst[i], n = s_upn[i];
+        float acc = 0.0f;
+        for (int j = 0; j < n; ++j) acc = fmaf(w[j], s_np[first + j], acc);
+        // local_cost = 1 - nccf; += soft_min_f0 * lag * nccf
+        float c = __fadd_rn(1.0f, -acc);
+        c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
+        s_new[i] = c;                  // holds the local cost until the state is finalised
       }
       // ---- exact Viterbi step: min_j pen[|i-j|] + prev[j] (first minimal j) ----
       // The transition cost is convex in (i - j), so the minimising j is
@@ -485,30 +479,26 @@ __global__ void __launch_bounds__(kPitchThreads) pitch_track_kernel(const TrackA
       }
       __syncthreads();
       float lmin = FLT_MAX;
-#pragma unroll
-      for (int r = 0; r < kMaxStatesPerThread; ++r) {
-        const int i = tid + r * kPitchThreads;
-        if (i < ns) {
-          const int ta = i / kAnchor;
-          float best;
-          int bj;
-          if (i == ta * kAnchor || i == ns - 1) {
-            const int t = (i == ns - 1) ? nanchor - 1 : ta;
-            best = s_acost[t]; bj = s_abp[t];
-          } else {
-            const int jlo = s_abp[ta], jhi = s_abp[min(ta + 1, nanchor - 1)];
-            best = FLT_MAX; bj = jlo;
-            for (int j = jlo; j <= jhi; ++j) {
-              const int d = j > i ? j - i : i - j;
-              const float c = __fadd_rn(s_pen[d], s_prev[j]);
-              if (c < best) { best = c; bj = j; }
-            }
+      for (int i = tid; i < ns; i += kPitchThreads) {
+        const int ta = i / kAnchor;
+        float best;
+        int bj;
+        if (i == ta * kAnchor || i == ns - 1) {
+          const int t = (i == ns - 1) ? nanchor - 1 : ta;
+          best = s_acost[t]; bj = s_abp[t];
+        } else {
+          const int jlo = s_abp[ta], jhi = s_abp[min(ta + 1, nanchor - 1)];
+          best = FLT_MAX; bj = jlo;
+          for (int j = jlo; j <= jhi; ++j) {
+            const int d = j > i ? j - i : i - j;
+            const float c = __fadd_rn(s_pen[d], s_prev[j]);
+            if (c < best) { best = c; bj = j; }
           }
-          bp[f * ns + i] = static_cast<int16_t>(bj);
-          const float v = __fadd_rn(best, lc[r]);
-          s_new[i] = v;
-          lmin = fminf(lmin, v);
         }
+        bp[f * ns + i] = static_cast<int16_t>(bj);
+        const float v = __fadd_rn(best, s_new[i]);      // + local cost (own slot)
+        s_new[i] = v;
+        lmin = fminf(lmin, v);
       }
       // block min -> renormalise so the smallest forward cost is zero
 #pragma unroll

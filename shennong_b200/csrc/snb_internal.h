@@ -124,6 +124,7 @@ struct snb_plan {
   bool fast_path = false;
   snb::FeatParams params;
   int32_t tile_frames = 32;
+  int32_t fused_occ = 3;     // CTAs per SM the fused kernel variant is compiled for
   void *d_tables = nullptr;  // one allocation holding all fixed tables
   size_t smem_bytes = 0;
   // VTLN mel-blob cache (host side), keyed by warp bits
