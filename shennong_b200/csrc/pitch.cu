@@ -316,7 +316,10 @@ __device__ __forceinline__ double block_sum_f64(double v, double *s_red) {
   return t;
 }
 
-__global__ void __launch_bounds__(kPitchThreads, 4) pitch_track_kernel(const TrackArgs a) {
+#ifndef SNB_PITCH_MINB
+#define SNB_PITCH_MINB 4
+#endif
+__global__ void __launch_bounds__(kPitchThreads, SNB_PITCH_MINB) pitch_track_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_win = reinterpret_cast<float *>(smem_raw);          // [full_len]
   float *s_np = s_win + a.full_len;                             // nccf_pitch [nmeas]
@@ -487,7 +490,8 @@ __global__ void __launch_bounds__(kPitchThreads, 4) pitch_track_kernel(const Tra
           const int t = (i == ns - 1) ? nanchor - 1 : ta;
           best = s_acost[t]; bj = s_abp[t];
         } else {
-          const int jlo = s_abp[ta], jhi = s_abp[min(ta + 1, nanchor - 1)];
+          const int ja = s_abp[ta], jb = s_abp[min(ta + 1, nanchor - 1)];
+          const int jlo = min(ja, jb), jhi = max(ja, jb);
           best = FLT_MAX; bj = jlo;
           for (int j = jlo; j <= jhi; ++j) {
             const int d = j > i ? j - i : i - j;
@@ -549,6 +553,273 @@ __global__ void __launch_bounds__(kPitchThreads, 4) pitch_track_kernel(const Tra
       o[1] = __fdiv_rn(1.0f, s_lags[s]);
     }
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k2': warp-per-utterance tracker (default).  Same arithmetic as
+// pitch_track_kernel, but each warp owns one utterance: no block barriers in
+// the frame loop (only __syncwarp), 8 independent utterances per CTA, window
+// energies from a double prefix sum (one pass instead of one per lag) and a
+// 3-level monotone Viterbi step (strides kA1, kA2, 1).
+// ---------------------------------------------------------------------------
+constexpr int kTrackWarps = 8;
+constexpr int kA1 = 64, kA2 = 8;
+
+struct WarpSmem {           // per-warp float offsets
+  int win, pre, np, nv, prev, cost, abp, total;
+};
+
+__host__ __device__ inline WarpSmem warp_smem_layout(int full_len, int nm, int ns) {
+  WarpSmem w;
+  int off = 0;
+  w.win = off; off += (full_len + 3) / 4 * 4;
+  w.pre = off; off += 2 * ((full_len + 1 + 1) / 2 * 2);      // doubles (as float pairs)
+  w.np = off; off += (nm + 3) / 4 * 4;
+  w.nv = off; off += (nm + 3) / 4 * 4;
+  w.prev = off; off += (ns + 3) / 4 * 4;
+  w.cost = off; off += (ns + 3) / 4 * 4;
+  w.abp = off; off += (ns + 3) / 4 * 4;                       // int backpointers of this frame
+  w.total = (off + 3) / 4 * 4;
+  return w;
+}
+
+__device__ __forceinline__ void warp_argmin(float &best, int &bj) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(SNB_FULL_MASK, best, o);
+    const int oj = __shfl_xor_sync(SNB_FULL_MASK, bj, o);
+    if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+  }
+}
+
+__global__ void __launch_bounds__(kTrackWarps * 32, 3) pitch_track_warp_kernel(const TrackArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = a.nstates, nm = a.nmeas, bl = a.basic_len, fl = a.full_len;
+  // ---- CTA-shared tables ----
+  float *s_pen = reinterpret_cast<float *>(smem_raw);
+  float *s_lags = s_pen + ns;
+  float *s_upw = s_lags + ns;
+  int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + ns * a.up_nw_max);
+  int32_t *s_upn = s_upfirst + ns;
+  for (int i = tid; i < ns; i += blockDim.x) {
+    s_pen[i] = a.pen[i]; s_lags[i] = a.lags[i];
+    s_upfirst[i] = a.up_first[i]; s_upn[i] = a.up_nw[i];
+  }
+  for (int i = tid; i < ns * a.up_nw_max; i += blockDim.x) s_upw[i] = a.up_w[i];
+  __syncthreads();
+  // ---- warp-private buffers ----
+  const WarpSmem L = warp_smem_layout(fl, nm, ns);
+  const int shared_floats = ((2 * ns + ns * a.up_nw_max + 2 * ns) + 3) / 4 * 4;
+  float *wbase = reinterpret_cast<float *>(smem_raw) + shared_floats + warp * L.total;
+  float *w_win = wbase + L.win;
+  double *w_pre = reinterpret_cast<double *>(wbase + L.pre);
+  float *w_np = wbase + L.np, *w_nv = wbase + L.nv;
+  float *w_prev = wbase + L.prev, *w_cost = wbase + L.cost;
+  int *w_bp = reinterpret_cast<int *>(wbase + L.abp);
+
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * kTrackWarps + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kTrackWarps;
+  int16_t *bp = a.bp + gw * a.max_frames * ns;
+  float *pov_raw = a.pov_raw + gw * a.max_frames * nm;
+  int32_t *states = a.states + gw * a.max_frames;
+
+  for (int64_t u = gw; u < a.nutts; u += nwarps) {
+    const int64_t doff = a.info[4 * u], m1 = a.info[4 * u + 1], m2 = a.info[4 * u + 2],
+                  end1 = a.info[4 * u + 3];
+    const int64_t row0 = a.frame_offsets[u], F = a.frame_offsets[u + 1] - row0;
+    if (F <= 0) continue;
+    const float *x = a.down + doff;
+    // ---- global mean-square for the ballast (double sums, two phases) ----
+    double p1 = 0.0, q1 = 0.0, p2 = 0.0, q2 = 0.0;
+    for (int64_t i = lane; i < m2; i += 32) {
+      const double v = x[i];
+      if (i < m1) { p1 += v; q1 += v * v; } else { p2 += v; q2 += v * v; }
+    }
+    p1 = group_sum_f64<32>(p1); q1 = group_sum_f64<32>(q1);
+    p2 = group_sum_f64<32>(p2); q2 = group_sum_f64<32>(q2);
+    const double sum2 = p1 + p2, sq2 = q1 + q2;
+    const double ms1 = m1 > 0 ? q1 / static_cast<double>(m1) - (p1 / static_cast<double>(m1)) * (p1 / static_cast<double>(m1)) : 0.0;
+    const double ms2 = m2 > 0 ? sq2 / static_cast<double>(m2) - (sum2 / static_cast<double>(m2)) * (sum2 / static_cast<double>(m2)) : 0.0;
+    const float ballast1 = static_cast<float>((ms1 * bl) * (ms1 * bl) * static_cast<double>(a.nccf_ballast));
+    const float ballast2 = static_cast<float>((ms2 * bl) * (ms2 * bl) * static_cast<double>(a.nccf_ballast));
+    for (int i = lane; i < ns; i += 32) w_prev[i] = 0.0f;
+    __syncwarp();
+
+    for (int64_t f = 0; f < F; ++f) {
+      const bool phase2 = f >= end1;
+      const int64_t avail = phase2 ? m2 : m1;
+      const float ballast = phase2 ? ballast2 : ballast1;
+      int64_t start;
+      if (a.snip_edges) start = f * a.shift;
+      else start = static_cast<int64_t>((static_cast<double>(f) + 0.5) * a.shift) - fl / 2;
+      // ---- ExtractFrame ----
+      for (int i = lane; i < fl; i += 32) {
+        const int64_t k = start + i;
+        w_win[i] = (k >= 0 && k < avail) ? x[k] : 0.0f;
+      }
+      __syncwarp();
+      if (a.preemph != 0.0f) {
+        for (int base = ((fl - 1) / 32) * 32; base >= 0; base -= 32) {   // downwards: original neighbours
+          const int i = base + lane;
+          float v = 0.0f;
+          if (i < fl) v = (i > 0) ? fmaf(-a.preemph, w_win[i - 1], w_win[i]) : w_win[0] * (1.0f - a.preemph);
+          __syncwarp();
+          if (i < fl) w_win[i] = v;
+          __syncwarp();
+        }
+      }
+      // ---- mean of the first basic_len samples, subtracted from the whole window ----
+      float sacc = 0.0f;
+      for (int i = lane; i < bl; i += 32) sacc += w_win[i];
+      const float mean = __fdiv_rn(group_sum<32>(sacc), static_cast<float>(bl));
+      // ---- zero-mean window + double prefix sums of squares: pre[k] = sum_{i<k} z_i^2 ----
+      {
+        const int chunk = (fl + 31) / 32;
+        const int i0 = lane * chunk, i1 = min(fl, i0 + chunk);
+        double local = 0.0;
+        for (int i = i0; i < i1; ++i) {
+          const float z = w_win[i] - mean;
+          w_win[i] = z;
+          local += static_cast<double>(z) * z;
+        }
+        double incl = local;                       // inclusive scan over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(SNB_FULL_MASK, incl, o);
+          if (lane >= o) incl += up;
+        }
+        double run = incl - local;                 // exclusive
+        for (int i = i0; i < i1; ++i) {
+          w_pre[i] = run;
+          run += static_cast<double>(w_win[i]) * w_win[i];
+        }
+        if (i1 == fl && i0 < fl) w_pre[fl] = run;
+      }
+      __syncwarp();
+      const float e1 = static_cast<float>(w_pre[bl] - w_pre[0]);
+      // ---- NCCF at the integer lags ----
+      for (int l = lane; l < nm; l += 32) {
+        const int lag = a.first_lag + l;
+        float inner = 0.0f;
+        int i = 0;
+        for (; i + 3 < bl; i += 4) {
+          inner = fmaf(w_win[i], w_win[lag + i], inner);
+          inner = fmaf(w_win[i + 1], w_win[lag + i + 1], inner);
+          inner = fmaf(w_win[i + 2], w_win[lag + i + 2], inner);
+          inner = fmaf(w_win[i + 3], w_win[lag + i + 3], inner);
+        }
+        for (; i < bl; ++i) inner = fmaf(w_win[i], w_win[lag + i], inner);
+        const float e2 = static_cast<float>(w_pre[lag + bl] - w_pre[lag]);
+        const float norm = __fmul_rn(e1, e2);
+        const float den_p = sqrtf(__fadd_rn(norm, ballast));
+        const float den_v = sqrtf(norm);
+        w_np[l] = den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f;
+        const float pv = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
+        w_nv[l] = pv;
+        pov_raw[f * nm + l] = pv;
+      }
+      __syncwarp();
+      // ---- upsample to the log-spaced lags; local cost ----
+      for (int i = lane; i < ns; i += 32) {
+        const float *w = s_upw + i * a.up_nw_max;
+        const int first = s_upfirst[i], n = s_upn[i];
+        float acc = 0.0f;
+        for (int j = 0; j < n; ++j) acc = fmaf(w[j], w_np[first + j], acc);
+        float c = __fadd_rn(1.0f, -acc);
+        c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
+        w_cost[i] = c;
+      }
+      __syncwarp();
+      // ---- Viterbi step, 3 monotone levels; w_bp[i] = backpointer of state i ----
+      // level 1: states 0, kA1, 2 kA1, ..., ns-1 scan every j (whole warp per state)
+      const int n1 = (ns - 1 + kA1 - 1) / kA1 + 1;
+      for (int t = 0; t < n1; ++t) {
+        const int i = min(t * kA1, ns - 1);
+        float best = FLT_MAX;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < ns; j += 32) {
+          const int d = j > i ? j - i : i - j;
+          const float c = __fadd_rn(s_pen[d], w_prev[j]);
+          if (c < best) { best = c; bj = j; }
+        }
+        warp_argmin(best, bj);
+        if (lane == 0) w_bp[i] = bj;
+      }
+      __syncwarp();
+      // level 2: multiples of kA2 between level-1 anchors: lane per state, bounded scan
+      for (int i = lane * kA2; i < ns - 1; i += 32 * kA2) {
+        if (i % kA1 == 0) continue;
+        const int left = (i / kA1) * kA1, right = min(left + kA1, ns - 1);
+        // (min/max: a float near-tie may break the monotonicity by one state)
+        const int jlo = min(w_bp[left], w_bp[right]), jhi = max(w_bp[left], w_bp[right]);
+        float best = FLT_MAX;
+        int bj = jlo;
+        for (int j = jlo; j <= jhi; ++j) {
+          const int d = j > i ? j - i : i - j;
+          const float c = __fadd_rn(s_pen[d], w_prev[j]);
+          if (c < best) { best = c; bj = j; }
+        }
+        w_bp[i] = bj;
+      }
+      __syncwarp();
+      // level 3: everything else between level-2 anchors; finalise all states
+      float lmin = FLT_MAX;
+      for (int i = lane; i < ns; i += 32) {
+        int bj;
+        float best;
+        if (i % kA2 == 0 || i == ns - 1) {
+          bj = w_bp[i];
+          const int d = bj > i ? bj - i : i - bj;
+          best = __fadd_rn(s_pen[d], w_prev[bj]);
+        } else {
+          const int left = (i / kA2) * kA2, right = min(left + kA2, ns - 1);
+          const int jlo = min(w_bp[left], w_bp[right]), jhi = max(w_bp[left], w_bp[right]);
+          best = FLT_MAX; bj = jlo;
+          for (int j = jlo; j <= jhi; ++j) {
+            const int d = j > i ? j - i : i - j;
+            const float c = __fadd_rn(s_pen[d], w_prev[j]);
+            if (c < best) { best = c; bj = j; }
+          }
+        }
+        bp[f * ns + i] = static_cast<int16_t>(bj);
+        const float v = __fadd_rn(best, w_cost[i]);
+        w_cost[i] = v;
+        lmin = fminf(lmin, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(SNB_FULL_MASK, lmin, o));
+      __syncwarp();
+      for (int i = lane; i < ns; i += 32) w_prev[i] = __fadd_rn(w_cost[i], -lmin);
+      __syncwarp();
+    }
+    // ---- best final state (first minimum), backtrace, output rows ----
+    float best = FLT_MAX;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < ns; i += 32)
+      if (w_prev[i] < best) { best = w_prev[i]; bi = i; }
+    warp_argmin(best, bi);
+    if (lane == 0) {
+      int sidx = bi;
+      for (int64_t f = F - 1; f >= 0; --f) {
+        states[f] = sidx;
+        sidx = bp[f * ns + sidx];
+      }
+    }
+    __syncwarp();
+    __threadfence_block();
+    for (int64_t f = lane; f < F; f += 32) {
+      const int sidx = states[f];
+      const float *w = s_upw + sidx * a.up_nw_max;
+      const float *pv = pov_raw + f * nm + s_upfirst[sidx];
+      float acc = 0.0f;
+      for (int j = 0; j < s_upn[sidx]; ++j) acc = fmaf(w[j], pv[j], acc);
+      float *o = a.out + (row0 + f) * a.ld_out;
+      o[0] = acc;
+      o[1] = __fdiv_rn(1.0f, s_lags[sidx]);
+    }
+    __syncwarp();
   }
 }
 
@@ -652,6 +923,40 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
 
 static size_t track_smem(const PitchTables *t);
 
+static size_t warp_track_smem(const PitchTables *t) {
+  const WarpSmem L = warp_smem_layout(t->full_len, t->nmeas, t->nstates);
+  const size_t shared_floats = ((2 * t->nstates + t->nstates * t->up_nw_max + 2 * t->nstates) + 3) / 4 * 4;
+  return (shared_floats + static_cast<size_t>(kTrackWarps) * L.total) * 4 + 16;
+}
+
+static bool use_warp_tracker(const PitchTables *t) {
+  static const bool disabled = getenv("SNB_PITCH_CTA") != nullptr;
+  return !disabled && warp_track_smem(t) <= 200 * 1024;
+}
+
+// number of concurrently tracked utterances ("slots" of per-utterance scratch)
+static int64_t pitch_slots(const PitchTables *t, int64_t nutts, int *grid_out) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  const size_t smem = warp_track_smem(t);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(pitch_track_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(smem));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pitch_track_warp_kernel, kTrackWarps * 32,
+                                                    smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int64_t want = (nutts + kTrackWarps - 1) / kTrackWarps;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sms) * per_sm)));
+  if (grid_out) *grid_out = grid;
+  return static_cast<int64_t>(grid) * kTrackWarps;
+}
+
 // persistent CTAs: exactly what is resident at once (a larger grid would run a
 // second, underfilled wave)
 static int pitch_grid(const PitchTables *t, int64_t nutts) {
@@ -714,7 +1019,8 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 extern "C" int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
   if (!plan || plan->kind != 1 || !batch) return -1;
   const PitchTables *t = plan->pitch;
-  const int64_t grid = pitch_grid(t, batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
+  const int64_t grid = use_warp_tracker(t) ? pitch_slots(t, batch->nutts, nullptr) : pitch_grid(t, batch->nutts);
+  const int64_t mf = std::max<int64_t>(1, max_frames_of(batch));
   size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4);
   bytes += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
   bytes += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
@@ -733,7 +1039,10 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
     return set_error(SNB_ERR_VALUE, "pitch workspace too small");
   const PitchTables *t = plan->pitch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int64_t grid = pitch_grid(t, batch->nutts), mf = std::max<int64_t>(1, max_frames_of(batch));
+  const bool warp_path = use_warp_tracker(t);
+  int warp_grid = 1;
+  const int64_t grid = warp_path ? pitch_slots(t, batch->nutts, &warp_grid) : pitch_grid(t, batch->nutts);
+  const int64_t mf = std::max<int64_t>(1, max_frames_of(batch));
   unsigned char *ws = static_cast<unsigned char *>(d_workspace);
   float *down = reinterpret_cast<float *>(ws);
   ws += align256(static_cast<size_t>(batch->total_down + 8) * 4);
@@ -773,6 +1082,11 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   a.bp = bp; a.pov_raw = pov_raw; a.states = states;
   a.max_frames = mf;
   a.out = d_out; a.ld_out = ld_out;
+  if (warp_path) {
+    pitch_track_warp_kernel<<<static_cast<unsigned>(warp_grid), kTrackWarps * 32, warp_track_smem(t), stream>>>(a);
+    SNB_LAUNCH_CHECK();
+    return SNB_OK;
+  }
   const size_t smem = track_smem(t);
   {
     static std::atomic<size_t> cur{48 * 1024};
