@@ -303,6 +303,7 @@ struct TrackArgs {
   int64_t max_frames;
   float *out;
   int64_t ld_out;
+  unsigned long long *queue;   // warp tracker: next utterance to hand out (zeroed before the launch)
 };
 
 __device__ __forceinline__ double block_sum_f64(double v, double *s_red) {
@@ -559,29 +560,68 @@ __global__ void __launch_bounds__(kPitchThreads, SNB_PITCH_MINB) pitch_track_ker
 // ---------------------------------------------------------------------------
 // k2': warp-per-utterance tracker (default).  Same arithmetic as
 // pitch_track_kernel, but each warp owns one utterance: no block barriers in
-// the frame loop (only __syncwarp), 8 independent utterances per CTA, window
-// energies from a double prefix sum (one pass instead of one per lag) and a
-// 3-level monotone Viterbi step (strides kA1, kA2, 1).
+// the frame loop (only __syncwarp), up to 24 independent utterances per CTA
+// (one CTA per SM, tables shared), utterances handed out through an atomic
+// queue, window energies from a double prefix sum (one pass instead of one per
+// lag), three NCCF lags per lane in flight, and a monotone divide-and-conquer
+// Viterbi step.
+//
+// Viterbi step: bp(i) = first argmin_j pen[|i-j|] + prev[j] is non-decreasing
+// in i (the penalty is convex), so bp(i) lies in [bp(i-s), bp(i+s)].
+//   * anchors (multiples of kA1 and the last state): whole-warp scans, the
+//     first and the last over every j, the others in bisection order over the
+//     range left by their neighbours;
+//   * levels s = kA1/2 ... 1: lane per state i = s(2k+1), serial scan of
+//     [bp(i-s), bp(i+s)] -- 1-3 candidates on the plateaus of bp, 2s+1 where bp
+//     follows i; the few states that straddle a jump of bp (range > 2s+2) are
+//     handed to whole-warp scans instead of stalling their round.
+// Every scan keeps the first minimum of its range, exactly like the
+// brute-force reference step (oracle/kaldi_oracle.c, orc_compute_pitch).
 // ---------------------------------------------------------------------------
-constexpr int kTrackWarps = 8;
-constexpr int kA1 = 64, kA2 = 8;
+constexpr int kTrackWarpsMax = 20;   // (24 fit in shared memory but run erratically slower)
+constexpr int kA1Log2 = 6, kA1 = 1 << kA1Log2;
 
 struct WarpSmem {           // per-warp float offsets
   int win, pre, np, nv, prev, cost, abp, total;
 };
 
-__host__ __device__ inline WarpSmem warp_smem_layout(int full_len, int nm, int ns) {
+// backpointers of the current frame are read with strides 2s: skew the index
+__host__ __device__ inline int bp_slot(int i) { return i + (i >> 5); }
+
+__host__ __device__ inline WarpSmem warp_smem_layout(int full_len, int nm, int ns, int nw_max) {
   WarpSmem w;
   int off = 0;
-  w.win = off; off += (full_len + 3) / 4 * 4;
+  w.win = off; off += (full_len + 4 + 3) / 4 * 4;             // + padding read by the NCCF loop
   w.pre = off; off += 2 * ((full_len + 1 + 1) / 2 * 2);      // doubles (as float pairs)
-  w.np = off; off += (nm + 3) / 4 * 4;
+  w.np = off; off += (nm + nw_max + 3) / 4 * 4;               // + zero tail for the padded taps
   w.nv = off; off += (nm + 3) / 4 * 4;
   w.prev = off; off += (ns + 3) / 4 * 4;
   w.cost = off; off += (ns + 3) / 4 * 4;
-  w.abp = off; off += (ns + 3) / 4 * 4;                       // int backpointers of this frame
+  w.abp = off; off += (bp_slot(ns) + 4) / 4 * 4;              // int backpointers of this frame
   w.total = (off + 3) / 4 * 4;
   return w;
+}
+
+__host__ __device__ inline int warp_shared_floats(int ns, int nw_max) {
+  return ((2 * ns + ns * (nw_max | 1) + ns) + 3) / 4 * 4;     // pen, lags, up_w (odd row stride), up_first
+}
+
+// first argmin over j in [jlo, jhi] of pen[|i-j|] + prev[j], by the whole warp.
+// Costs are non-negative floats (pen >= 0, prev >= 0): their bit patterns order
+// like integers, so the warp minimum is one REDUX (then one more for the
+// smallest j among the lanes that hold it: the first minimum).
+__device__ __forceinline__ int coop_scan(const float *s_pen, const float *w_prev, int i, int jlo, int jhi,
+                                         int lane) {
+  int best = 0x7f7fffff;          // FLT_MAX
+  int bj = 0x7fffffff;
+#pragma unroll 1
+  for (int j = jlo + lane; j <= jhi; j += 32) {
+    const int d = j > i ? j - i : i - j;
+    const int c = __float_as_int(__fadd_rn(s_pen[d], w_prev[j]));
+    if (c < best) { best = c; bj = j; }
+  }
+  const int m = __reduce_min_sync(SNB_FULL_MASK, best);
+  return __reduce_min_sync(SNB_FULL_MASK, best == m ? bj : 0x7fffffff);
 }
 
 __device__ __forceinline__ void warp_argmin(float &best, int &bj) {
@@ -593,49 +633,58 @@ __device__ __forceinline__ void warp_argmin(float &best, int &bj) {
   }
 }
 
-__global__ void __launch_bounds__(kTrackWarps * 32, 3) pitch_track_warp_kernel(const TrackArgs a) {
+template <int NWC>   // NWC > 0: number of upsampling taps known at compile time
+__global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarp_cta = blockDim.x >> 5;
   const int ns = a.nstates, nm = a.nmeas, bl = a.basic_len, fl = a.full_len;
+  const int nw = NWC > 0 ? NWC : a.up_nw_max;
+  const int nwp = nw | 1;                                     // odd row stride: conflict-free
   // ---- CTA-shared tables ----
   float *s_pen = reinterpret_cast<float *>(smem_raw);
   float *s_lags = s_pen + ns;
-  float *s_upw = s_lags + ns;
-  int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + ns * a.up_nw_max);
-  int32_t *s_upn = s_upfirst + ns;
+  float *s_upw = s_lags + ns;                                 // [ns][nwp]
+  int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + ns * nwp);
   for (int i = tid; i < ns; i += blockDim.x) {
     s_pen[i] = a.pen[i]; s_lags[i] = a.lags[i];
-    s_upfirst[i] = a.up_first[i]; s_upn[i] = a.up_nw[i];
+    s_upfirst[i] = min(max(a.up_first[i], 0), nm - 1);         // (a state without taps has zero weights)
   }
-  for (int i = tid; i < ns * a.up_nw_max; i += blockDim.x) s_upw[i] = a.up_w[i];
+  for (int i = tid; i < ns * nw; i += blockDim.x) s_upw[(i / nw) * nwp + i % nw] = a.up_w[i];
   __syncthreads();
   // ---- warp-private buffers ----
-  const WarpSmem L = warp_smem_layout(fl, nm, ns);
-  const int shared_floats = ((2 * ns + ns * a.up_nw_max + 2 * ns) + 3) / 4 * 4;
-  float *wbase = reinterpret_cast<float *>(smem_raw) + shared_floats + warp * L.total;
+  const WarpSmem L = warp_smem_layout(fl, nm, ns, nw);
+  float *wbase = reinterpret_cast<float *>(smem_raw) + warp_shared_floats(ns, nw) + warp * L.total;
   float *w_win = wbase + L.win;
   double *w_pre = reinterpret_cast<double *>(wbase + L.pre);
   float *w_np = wbase + L.np, *w_nv = wbase + L.nv;
   float *w_prev = wbase + L.prev, *w_cost = wbase + L.cost;
   int *w_bp = reinterpret_cast<int *>(wbase + L.abp);
 
-  const int64_t gw = static_cast<int64_t>(blockIdx.x) * kTrackWarps + warp;
-  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kTrackWarps;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * nwarp_cta + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * nwarp_cta;
   int16_t *bp = a.bp + gw * a.max_frames * ns;
   float *pov_raw = a.pov_raw + gw * a.max_frames * nm;
   int32_t *states = a.states + gw * a.max_frames;
+  const int n1 = (ns - 1 + kA1 - 1) / kA1 + 1;                // anchors min(t kA1, ns-1), t < n1
+  int top = 1;
+  while (top < n1) top <<= 1;
+  for (int i = nm + lane; i < nm + nw; i += 32) w_np[i] = 0.0f;
+  if (lane < 4) w_win[fl + lane] = 0.0f;
 
-  for (int64_t u = gw; u < a.nutts; u += nwarps) {
+  int64_t u = gw;
+  while (u < a.nutts) {
     const int64_t doff = a.info[4 * u], m1 = a.info[4 * u + 1], m2 = a.info[4 * u + 2],
                   end1 = a.info[4 * u + 3];
     const int64_t row0 = a.frame_offsets[u], F = a.frame_offsets[u + 1] - row0;
-    if (F <= 0) continue;
     const float *x = a.down + doff;
     // ---- global mean-square for the ballast (double sums, two phases) ----
     double p1 = 0.0, q1 = 0.0, p2 = 0.0, q2 = 0.0;
-    for (int64_t i = lane; i < m2; i += 32) {
-      const double v = x[i];
-      if (i < m1) { p1 += v; q1 += v * v; } else { p2 += v; q2 += v * v; }
+    if (F > 0) {
+      for (int64_t i = lane; i < m2; i += 32) {
+        const double v = x[i];
+        if (i < m1) { p1 += v; q1 += v * v; } else { p2 += v; q2 += v * v; }
+      }
     }
     p1 = group_sum_f64<32>(p1); q1 = group_sum_f64<32>(q1);
     p2 = group_sum_f64<32>(p2); q2 = group_sum_f64<32>(q2);
@@ -699,92 +748,137 @@ __global__ void __launch_bounds__(kTrackWarps * 32, 3) pitch_track_warp_kernel(c
       }
       __syncwarp();
       const float e1 = static_cast<float>(w_pre[bl] - w_pre[0]);
-      // ---- NCCF at the integer lags ----
-      for (int l = lane; l < nm; l += 32) {
-        const int lag = a.first_lag + l;
-        float inner = 0.0f;
+      // ---- NCCF at the integer lags: lane = three consecutive lags; the window
+      //      samples w[lag+i..] slide through six registers (4 new loads per 12 FMAs) ----
+#pragma unroll 1
+      for (int lb = 0; lb < nm; lb += 96) {
+        const int l0 = lb + 3 * lane;
+        const float *q = w_win + a.first_lag + min(l0, nm - 1);   // (reads up to 2 floats of padding)
+        float in0 = 0.0f, in1 = 0.0f, in2 = 0.0f;
+        float r0 = q[0], r1 = q[1];
         int i = 0;
+#pragma unroll 1
         for (; i + 3 < bl; i += 4) {
-          inner = fmaf(w_win[i], w_win[lag + i], inner);
-          inner = fmaf(w_win[i + 1], w_win[lag + i + 1], inner);
-          inner = fmaf(w_win[i + 2], w_win[lag + i + 2], inner);
-          inner = fmaf(w_win[i + 3], w_win[lag + i + 3], inner);
+          const float4 w4 = *reinterpret_cast<const float4 *>(w_win + i);
+          const float r2 = q[i + 2], r3 = q[i + 3], r4 = q[i + 4], r5 = q[i + 5];
+          in0 = fmaf(w4.x, r0, in0); in1 = fmaf(w4.x, r1, in1); in2 = fmaf(w4.x, r2, in2);
+          in0 = fmaf(w4.y, r1, in0); in1 = fmaf(w4.y, r2, in1); in2 = fmaf(w4.y, r3, in2);
+          in0 = fmaf(w4.z, r2, in0); in1 = fmaf(w4.z, r3, in1); in2 = fmaf(w4.z, r4, in2);
+          in0 = fmaf(w4.w, r3, in0); in1 = fmaf(w4.w, r4, in1); in2 = fmaf(w4.w, r5, in2);
+          r0 = r4; r1 = r5;
         }
-        for (; i < bl; ++i) inner = fmaf(w_win[i], w_win[lag + i], inner);
-        const float e2 = static_cast<float>(w_pre[lag + bl] - w_pre[lag]);
-        const float norm = __fmul_rn(e1, e2);
-        const float den_p = sqrtf(__fadd_rn(norm, ballast));
-        const float den_v = sqrtf(norm);
-        w_np[l] = den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f;
-        const float pv = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
-        w_nv[l] = pv;
-        pov_raw[f * nm + l] = pv;
+        for (; i < bl; ++i) {
+          const float wv = w_win[i];
+          in0 = fmaf(wv, q[i], in0); in1 = fmaf(wv, q[i + 1], in1); in2 = fmaf(wv, q[i + 2], in2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int l = l0 + k;
+          const float inner = k == 0 ? in0 : (k == 1 ? in1 : in2);
+          if (l < nm) {
+            const int lag = a.first_lag + l;
+            const float e2 = static_cast<float>(w_pre[lag + bl] - w_pre[lag]);
+            const float norm = __fmul_rn(e1, e2);
+            const float den_p = sqrtf(__fadd_rn(norm, ballast));
+            const float den_v = sqrtf(norm);
+            w_np[l] = den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f;
+            const float pv = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
+            w_nv[l] = pv;
+            pov_raw[f * nm + l] = pv;
+          }
+        }
       }
       __syncwarp();
-      // ---- upsample to the log-spaced lags; local cost ----
+      // ---- upsample to the log-spaced lags (taps padded with zeros to nw); local cost ----
       for (int i = lane; i < ns; i += 32) {
-        const float *w = s_upw + i * a.up_nw_max;
-        const int first = s_upfirst[i], n = s_upn[i];
+        const float *src = w_np + s_upfirst[i];
+        const float *w = s_upw + i * nwp;
         float acc = 0.0f;
-        for (int j = 0; j < n; ++j) acc = fmaf(w[j], w_np[first + j], acc);
+        if (NWC > 0) {
+#pragma unroll
+          for (int j = 0; j < NWC; ++j) acc = fmaf(w[j], src[j], acc);
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < nw; ++j) acc = fmaf(w[j], src[j], acc);
+        }
         float c = __fadd_rn(1.0f, -acc);
         c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
         w_cost[i] = c;
       }
       __syncwarp();
-      // ---- Viterbi step, 3 monotone levels; w_bp[i] = backpointer of state i ----
-      // level 1: states 0, kA1, 2 kA1, ..., ns-1 scan every j (whole warp per state)
-      const int n1 = (ns - 1 + kA1 - 1) / kA1 + 1;
-      for (int t = 0; t < n1; ++t) {
-        const int i = min(t * kA1, ns - 1);
-        float best = FLT_MAX;
-        int bj = 0x7fffffff;
-        for (int j = lane; j < ns; j += 32) {
-          const int d = j > i ? j - i : i - j;
-          const float c = __fadd_rn(s_pen[d], w_prev[j]);
-          if (c < best) { best = c; bj = j; }
+      // ---- Viterbi step: anchors by whole-warp scans, bisection order ----
+      {
+        const int last = ns - 1;
+        int bj = coop_scan(s_pen, w_prev, 0, 0, last, lane);
+        if (lane == 0) w_bp[bp_slot(0)] = bj;
+        if (n1 > 1) {
+          bj = coop_scan(s_pen, w_prev, last, bj, last, lane);
+          if (lane == 0) w_bp[bp_slot(last)] = bj;
         }
-        warp_argmin(best, bj);
-        if (lane == 0) w_bp[i] = bj;
-      }
-      __syncwarp();
-      // level 2: multiples of kA2 between level-1 anchors: lane per state, bounded scan
-      for (int i = lane * kA2; i < ns - 1; i += 32 * kA2) {
-        if (i % kA1 == 0) continue;
-        const int left = (i / kA1) * kA1, right = min(left + kA1, ns - 1);
-        // (min/max: a float near-tie may break the monotonicity by one state)
-        const int jlo = min(w_bp[left], w_bp[right]), jhi = max(w_bp[left], w_bp[right]);
-        float best = FLT_MAX;
-        int bj = jlo;
-        for (int j = jlo; j <= jhi; ++j) {
-          const int d = j > i ? j - i : i - j;
-          const float c = __fadd_rn(s_pen[d], w_prev[j]);
-          if (c < best) { best = c; bj = j; }
+        __syncwarp();
+        for (int step = top >> 1; step >= 1; step >>= 1) {
+          for (int t = step; t < n1 - 1; t += 2 * step) {
+            const int i = t * kA1;
+            const int il = (t - step) * kA1, ir = min((t + step) * kA1, last);
+            const int b0 = w_bp[bp_slot(il)], b1 = w_bp[bp_slot(ir)];
+            // (min/max: a float near-tie may break the monotonicity by one state)
+            bj = coop_scan(s_pen, w_prev, i, min(b0, b1), max(b0, b1), lane);
+            if (lane == 0) w_bp[bp_slot(i)] = bj;
+          }
+          __syncwarp();
         }
-        w_bp[i] = bj;
       }
-      __syncwarp();
-      // level 3: everything else between level-2 anchors; finalise all states
+      // ---- levels kA1/2 ... 1: lane per state, long ranges by the whole warp ----
+#pragma unroll 1
+      for (int ls = kA1Log2 - 1; ls >= 0; --ls) {
+        const int s = 1 << ls;
+        const int nodd = (ns - 2 >= s) ? ((ns - 2 - s) >> (ls + 1)) + 1 : 0;
+        const int T = min(32, 2 * s + 2);
+#pragma unroll 1
+        for (int k0 = 0; k0 < nodd; k0 += 32) {
+          const int k = k0 + lane;
+          const bool act = k < nodd;
+          const int i = s * (2 * k + 1);
+          int jlo = 0, jhi = 0;
+          if (act) {
+            const int b0 = w_bp[bp_slot(i - s)], b1 = w_bp[bp_slot(min(i + s, ns - 1))];
+            jlo = min(b0, b1); jhi = max(b0, b1);
+          }
+          unsigned longm = __ballot_sync(SNB_FULL_MASK, jhi - jlo >= T);
+          int bj = jlo;
+          if (jhi > jlo && jhi - jlo < T) {
+            float best = FLT_MAX;
+            const float *pp = w_prev + jlo;
+            int d = jlo - i, bd = d;
+#pragma unroll 1
+            for (int n = jhi - jlo; n >= 0; --n) {
+              const float c = __fadd_rn(s_pen[d < 0 ? -d : d], *pp);
+              if (c < best) { best = c; bd = d; }
+              ++pp; ++d;
+            }
+            bj = i + bd;
+          }
+#pragma unroll 1
+          while (longm) {
+            const int src = __ffs(longm) - 1;
+            longm &= longm - 1u;
+            const int ci = __shfl_sync(SNB_FULL_MASK, i, src);
+            const int clo = __shfl_sync(SNB_FULL_MASK, jlo, src);
+            const int chi = __shfl_sync(SNB_FULL_MASK, jhi, src);
+            const int cb = coop_scan(s_pen, w_prev, ci, clo, chi, lane);
+            if (lane == src) bj = cb;
+          }
+          if (act) w_bp[bp_slot(i)] = bj;
+        }
+        __syncwarp();
+      }
+      // ---- forward costs, backpointers to global, renormalise ----
       float lmin = FLT_MAX;
       for (int i = lane; i < ns; i += 32) {
-        int bj;
-        float best;
-        if (i % kA2 == 0 || i == ns - 1) {
-          bj = w_bp[i];
-          const int d = bj > i ? bj - i : i - bj;
-          best = __fadd_rn(s_pen[d], w_prev[bj]);
-        } else {
-          const int left = (i / kA2) * kA2, right = min(left + kA2, ns - 1);
-          const int jlo = min(w_bp[left], w_bp[right]), jhi = max(w_bp[left], w_bp[right]);
-          best = FLT_MAX; bj = jlo;
-          for (int j = jlo; j <= jhi; ++j) {
-            const int d = j > i ? j - i : i - j;
-            const float c = __fadd_rn(s_pen[d], w_prev[j]);
-            if (c < best) { best = c; bj = j; }
-          }
-        }
+        const int bj = w_bp[bp_slot(i)];
+        const int d = bj > i ? bj - i : i - bj;
+        const float v = __fadd_rn(__fadd_rn(s_pen[d], w_prev[bj]), w_cost[i]);
         bp[f * ns + i] = static_cast<int16_t>(bj);
-        const float v = __fadd_rn(best, w_cost[i]);
         w_cost[i] = v;
         lmin = fminf(lmin, v);
       }
@@ -794,32 +888,41 @@ __global__ void __launch_bounds__(kTrackWarps * 32, 3) pitch_track_warp_kernel(c
       for (int i = lane; i < ns; i += 32) w_prev[i] = __fadd_rn(w_cost[i], -lmin);
       __syncwarp();
     }
-    // ---- best final state (first minimum), backtrace, output rows ----
-    float best = FLT_MAX;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < ns; i += 32)
-      if (w_prev[i] < best) { best = w_prev[i]; bi = i; }
-    warp_argmin(best, bi);
-    if (lane == 0) {
-      int sidx = bi;
-      for (int64_t f = F - 1; f >= 0; --f) {
-        states[f] = sidx;
-        sidx = bp[f * ns + sidx];
+    if (F > 0) {
+      // ---- best final state (first minimum), backtrace, output rows ----
+      float best = FLT_MAX;
+      int bi = 0x7fffffff;
+      for (int i = lane; i < ns; i += 32)
+        if (w_prev[i] < best) { best = w_prev[i]; bi = i; }
+      warp_argmin(best, bi);
+      if (lane == 0) {
+        int sidx = bi;
+        for (int64_t f = F - 1; f >= 0; --f) {
+          states[f] = sidx;
+          sidx = bp[f * ns + sidx];
+        }
       }
+      __syncwarp();
+      __threadfence_block();
+      for (int64_t f = lane; f < F; f += 32) {
+        const int sidx = states[f];
+        const float *w = s_upw + sidx * nwp;
+        const float *pv = pov_raw + f * nm + s_upfirst[sidx];
+        const int n = min(nw, nm - s_upfirst[sidx]);           // taps beyond are zero weights
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) acc = fmaf(w[j], pv[j], acc);
+        float *o = a.out + (row0 + f) * a.ld_out;
+        o[0] = acc;
+        o[1] = __fdiv_rn(1.0f, s_lags[sidx]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    __threadfence_block();
-    for (int64_t f = lane; f < F; f += 32) {
-      const int sidx = states[f];
-      const float *w = s_upw + sidx * a.up_nw_max;
-      const float *pv = pov_raw + f * nm + s_upfirst[sidx];
-      float acc = 0.0f;
-      for (int j = 0; j < s_upn[sidx]; ++j) acc = fmaf(w[j], pv[j], acc);
-      float *o = a.out + (row0 + f) * a.ld_out;
-      o[0] = acc;
-      o[1] = __fdiv_rn(1.0f, s_lags[sidx]);
-    }
-    __syncwarp();
+    // ---- next utterance from the queue ----
+    unsigned long long nxt = 0;
+    if (lane == 0) nxt = atomicAdd(a.queue, 1ULL);
+    nxt = __shfl_sync(SNB_FULL_MASK, nxt, 0);
+    u = nwarps + static_cast<int64_t>(nxt);
   }
 }
 
@@ -923,38 +1026,48 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
 
 static size_t track_smem(const PitchTables *t);
 
-static size_t warp_track_smem(const PitchTables *t) {
-  const WarpSmem L = warp_smem_layout(t->full_len, t->nmeas, t->nstates);
-  const size_t shared_floats = ((2 * t->nstates + t->nstates * t->up_nw_max + 2 * t->nstates) + 3) / 4 * 4;
-  return (shared_floats + static_cast<size_t>(kTrackWarps) * L.total) * 4 + 16;
+static size_t warp_track_smem(const PitchTables *t, int warps) {
+  const WarpSmem L = warp_smem_layout(t->full_len, t->nmeas, t->nstates, t->up_nw_max);
+  return (static_cast<size_t>(warp_shared_floats(t->nstates, t->up_nw_max)) +
+          static_cast<size_t>(warps) * L.total) * 4 + 16;
+}
+
+constexpr size_t kTrackSmemBudget = 224 * 1024;
+constexpr int kTrackWarpsMin = 4;
+
+// most warps (utterances in flight) one CTA can hold
+static int warp_track_capacity(const PitchTables *t) {
+  static const char *env = getenv("SNB_PITCH_WARPS");          // tuning knob: cap the warps per CTA
+  int w = kTrackWarpsMax;
+  if (env && atoi(env) >= kTrackWarpsMin) w = std::min(w, atoi(env) / 4 * 4);
+  while (w >= kTrackWarpsMin && warp_track_smem(t, w) > kTrackSmemBudget) w -= 4;
+  return w;
 }
 
 static bool use_warp_tracker(const PitchTables *t) {
   static const bool disabled = getenv("SNB_PITCH_CTA") != nullptr;
-  return !disabled && warp_track_smem(t) <= 200 * 1024;
+  return !disabled && warp_track_capacity(t) >= kTrackWarpsMin && t->nstates <= 32767;
 }
 
-// number of concurrently tracked utterances ("slots" of per-utterance scratch)
-static int64_t pitch_slots(const PitchTables *t, int64_t nutts, int *grid_out) {
-  int dev = 0, sms = 148, per_sm = 1;
+// warp tracker launch shape: one CTA per SM, as many warps per CTA as the batch
+// can feed (multiple of 4, up to the smem capacity); returns the number of
+// concurrently tracked utterances ("slots" of per-utterance scratch)
+static int64_t pitch_slots(const PitchTables *t, int64_t nutts, int *grid_out, int *warps_out) {
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
     cudaGetLastError();
     sms = 148;
   }
-  const size_t smem = warp_track_smem(t);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(pitch_track_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(smem));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pitch_track_warp_kernel, kTrackWarps * 32,
-                                                    smem) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    per_sm = 1;
-  }
-  const int64_t want = (nutts + kTrackWarps - 1) / kTrackWarps;
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sms) * per_sm)));
+  const int cap = warp_track_capacity(t);
+  int64_t w = (std::max<int64_t>(nutts, 1) + sms - 1) / sms;
+  w = (w + 3) / 4 * 4;
+  const int warps = static_cast<int>(std::max<int64_t>(kTrackWarpsMin, std::min<int64_t>(w, cap)));
+  const int64_t want = (std::max<int64_t>(nutts, 1) + warps - 1) / warps;
+  const int grid = static_cast<int>(std::min<int64_t>(want, sms));
   if (grid_out) *grid_out = grid;
-  return static_cast<int64_t>(grid) * kTrackWarps;
+  if (warps_out) *warps_out = warps;
+  return static_cast<int64_t>(grid) * warps;
 }
 
 // persistent CTAs: exactly what is resident at once (a larger grid would run a
@@ -1019,9 +1132,10 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 extern "C" int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
   if (!plan || plan->kind != 1 || !batch) return -1;
   const PitchTables *t = plan->pitch;
-  const int64_t grid = use_warp_tracker(t) ? pitch_slots(t, batch->nutts, nullptr) : pitch_grid(t, batch->nutts);
+  const int64_t grid = use_warp_tracker(t) ? pitch_slots(t, batch->nutts, nullptr, nullptr)
+                                           : pitch_grid(t, batch->nutts);
   const int64_t mf = std::max<int64_t>(1, max_frames_of(batch));
-  size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4);
+  size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4) + 256;   // + utterance queue
   bytes += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
   bytes += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
   bytes += align256(static_cast<size_t>(grid) * mf * 4);
@@ -1040,12 +1154,15 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   const PitchTables *t = plan->pitch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool warp_path = use_warp_tracker(t);
-  int warp_grid = 1;
-  const int64_t grid = warp_path ? pitch_slots(t, batch->nutts, &warp_grid) : pitch_grid(t, batch->nutts);
+  int warp_grid = 1, warp_count = kTrackWarpsMin;
+  const int64_t grid = warp_path ? pitch_slots(t, batch->nutts, &warp_grid, &warp_count)
+                                 : pitch_grid(t, batch->nutts);
   const int64_t mf = std::max<int64_t>(1, max_frames_of(batch));
   unsigned char *ws = static_cast<unsigned char *>(d_workspace);
   float *down = reinterpret_cast<float *>(ws);
   ws += align256(static_cast<size_t>(batch->total_down + 8) * 4);
+  unsigned long long *queue = reinterpret_cast<unsigned long long *>(ws);
+  ws += 256;
   int16_t *bp = reinterpret_cast<int16_t *>(ws);
   ws += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
   float *pov_raw = reinterpret_cast<float *>(ws);
@@ -1082,8 +1199,26 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   a.bp = bp; a.pov_raw = pov_raw; a.states = states;
   a.max_frames = mf;
   a.out = d_out; a.ld_out = ld_out;
+  a.queue = queue;
   if (warp_path) {
-    pitch_track_warp_kernel<<<static_cast<unsigned>(warp_grid), kTrackWarps * 32, warp_track_smem(t), stream>>>(a);
+    const size_t wsmem = warp_track_smem(t, warp_count);
+    static std::atomic<size_t> wcur{48 * 1024};
+    size_t c = wcur.load();
+    while (wsmem > c) {
+      cudaError_t e = cudaFuncSetAttribute(pitch_track_warp_kernel<10>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(pitch_track_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(wsmem));
+      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
+      if (wcur.compare_exchange_weak(c, wsmem)) break;
+    }
+    cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch queue: %s", cudaGetErrorString(e));
+    if (t->up_nw_max == 10)     // Kaldi's default resampling options
+      pitch_track_warp_kernel<10><<<static_cast<unsigned>(warp_grid), warp_count * 32, wsmem, stream>>>(a);
+    else
+      pitch_track_warp_kernel<0><<<static_cast<unsigned>(warp_grid), warp_count * 32, wsmem, stream>>>(a);
     SNB_LAUNCH_CHECK();
     return SNB_OK;
   }

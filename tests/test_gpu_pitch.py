@@ -31,7 +31,12 @@ def check_pitch(out, ref):
 @pytest.mark.parametrize('kwargs', [
     {}, {'min_f0': 60, 'max_f0': 350}, {'frame_shift': 0.02},
     {'frame_shift': 0.02, 'frame_length': 0.05}, {'penalty_factor': 0.3},
-    {'nccf_ballast': 1000, 'soft_min_f0': 20}])
+    {'nccf_ballast': 1000, 'soft_min_f0': 20},
+    # other table shapes: 1040 states (more Viterbi anchors, fewer warps per
+    # CTA), 139 states, generic tap count of the upsampling filter
+    {'delta_pitch': 0.002}, {'min_f0': 100, 'max_f0': 200},
+    {'upsample_filter_width': 7}, {'resample_freq': 3000,
+                                   'lowpass_cutoff': 700}])
 def test_pitch_test_wav(pcm, kwargs):
     out = KaldiPitchProcessor(**kwargs).process(Audio(pcm, 16000))
     ref = oracle.pitch(pcm, **kwargs)

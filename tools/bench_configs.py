@@ -1,5 +1,6 @@
 """Secondary measurements on one GPU for the other BASELINE.json configs
-(device-resident PCM, CUDA events, 3 warm-ups + 5 reps; not the bench.py line).
+(device-resident PCM, CUDA events around each of 5 reps after 3 warm-ups, median;
+host-side batch creation is inside the timed call; not the bench.py line).
 
     python tools/bench_configs.py [--utts N]
 """
@@ -68,22 +69,26 @@ def main():
 
         def run():
             return pipe.run_device(packed, speakers=speakers, plans=plans)
-        for _ in range(2):
+        for _ in range(3):
             out, offs, _, _ = run()
         torch.cuda.synchronize()
-        e0, e1 = (torch.cuda.Event(enable_timing=True),
-                  torch.cuda.Event(enable_timing=True))
-        reps = 3
-        e0.record()
+        reps = 5
+        times = []
         for _ in range(reps):
+            e0, e1 = (torch.cuda.Event(enable_timing=True),
+                      torch.cuda.Event(enable_timing=True))
+            e0.record()
             run()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times))
         frames = int(offs[-1])
-        results[name] = {'ms': ms, 'frames': frames, 'dim': int(out.shape[1]),
+        results[name] = {'ms': ms, 'ms_min': min(times), 'ms_max': max(times),
+                         'frames': frames, 'dim': int(out.shape[1]),
                          'frames_per_s': frames / (ms * 1e-3)}
-        print(f'{name:40s} {ms:9.3f} ms  {frames / (ms * 1e-3):.3e} frames/s '
+        print(f'{name:40s} {ms:9.3f} ms (min {min(times):.3f} max '
+              f'{max(times):.3f})  {frames / (ms * 1e-3):.3e} frames/s '
               f'D={out.shape[1]}', flush=True)
     print(json.dumps(results))
 
