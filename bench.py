@@ -331,11 +331,15 @@ def main():
         d2h_gbs = out.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del scratch
         nrep = max(2, min(args.steps, 5))
-        pipe.run_host(host_pcm, starts, lengths, out_host=out_host)  # warm-up
+        for _ in range(2):                                           # warm-up
+            pipe.run_host(host_pcm, starts, lengths, out_host=out_host)
         barrier()
+        rep_ms = []
         t_e0 = time.perf_counter()
         for _ in range(nrep):
+            t_r = time.perf_counter()
             pipe.run_host(host_pcm, starts, lengths, out_host=out_host)
+            rep_ms.append((time.perf_counter() - t_r) * 1e3)
         barrier()
         dt = (time.perf_counter() - t_e0) / nrep
         tt = torch.tensor([dt], device='cuda', dtype=torch.float64)
@@ -346,6 +350,7 @@ def main():
                'h2d_bytes_per_step': int(nutts * UTT_SAMPLES * 2),
                'd2h_bytes_per_step': int(total_frames * 39 * 4),
                'ms_per_step': dt * 1e3,
+               'ms_each_step': [round(t, 2) for t in rep_ms],
                'api': 'FusedPipeline.run_host (chunked H2D/compute/D2H)',
                'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs}
 

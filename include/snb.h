@@ -165,6 +165,18 @@ int32_t snb_plan_uses_fast_path(const snb_plan *plan);
 int snb_batch_create(const snb_plan *plan, const int64_t *sample_begin,
                      const int64_t *sample_len, int64_t nutts,
                      const float *vtln_warps, snb_batch **out);
+/* Stream-ordered variant for chunked pipelines: the descriptor upload is
+ * queued on `stream` (no host wait, no cudaMalloc/cudaFree in the steady state:
+ * device blob and pinned staging come from internal pools) and
+ * snb_batch_destroy() recycles the blob once the work queued -- up to the
+ * destroy call -- on `stream` and on every stream given to a compute call with
+ * this batch has drained.  Contract: kernels that read the batch (including
+ * post-processing calls given snb_batch_frame_offsets_device()) are queued on
+ * one of those streams before the batch is destroyed. */
+int snb_batch_create_on_stream(const snb_plan *plan, const int64_t *sample_begin,
+                               const int64_t *sample_len, int64_t nutts,
+                               const float *vtln_warps, void *stream,
+                               snb_batch **out);
 void snb_batch_destroy(snb_batch *batch);
 int64_t snb_batch_num_utts(const snb_batch *batch);
 int64_t snb_batch_total_frames(const snb_batch *batch);

@@ -104,6 +104,8 @@ SIGNATURES = {
     'snb_plan_dim': (i32, [vp]),
     'snb_plan_uses_fast_path': (i32, [vp]),
     'snb_batch_create': (ctypes.c_int, [vp, vp, vp, i64, vp, vp]),
+    'snb_batch_create_on_stream': (ctypes.c_int,
+                                   [vp, vp, vp, i64, vp, vp, vp]),
     'snb_batch_destroy': (None, [vp]),
     'snb_batch_num_utts': (i64, [vp]),
     'snb_batch_total_frames': (i64, [vp]),

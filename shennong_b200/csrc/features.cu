@@ -1123,9 +1123,26 @@ extern "C" int32_t snb_plan_uses_fast_path(const snb_plan *plan) { return plan->
 // ---------------------------------------------------------------------------
 // host: batch
 // ---------------------------------------------------------------------------
+static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, const int64_t *sample_len,
+                             int64_t nutts, const float *vtln_warps, bool on_stream, cudaStream_t stream,
+                             snb_batch **out);
+
 extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begin,
                                 const int64_t *sample_len, int64_t nutts, const float *vtln_warps,
                                 snb_batch **out) {
+  return batch_create_impl(plan, sample_begin, sample_len, nutts, vtln_warps, false, nullptr, out);
+}
+
+extern "C" int snb_batch_create_on_stream(const snb_plan *plan, const int64_t *sample_begin,
+                                          const int64_t *sample_len, int64_t nutts, const float *vtln_warps,
+                                          void *stream, snb_batch **out) {
+  return batch_create_impl(plan, sample_begin, sample_len, nutts, vtln_warps, true,
+                           static_cast<cudaStream_t>(stream), out);
+}
+
+static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, const int64_t *sample_len,
+                             int64_t nutts, const float *vtln_warps, bool on_stream, cudaStream_t stream,
+                             snb_batch **out) {
   if (!plan || !out || nutts < 0 || (nutts > 0 && (!sample_begin || !sample_len)))
     return set_error(SNB_ERR_VALUE, "bad argument");
   *out = nullptr;
@@ -1225,11 +1242,40 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
     }
   }
   unsigned char *d = nullptr;
-  cudaError_t e = cudaMalloc(&d, stage.size() + 16);
-  if (e == cudaSuccess) e = upload(d, stage.data(), stage.size());
-  if (e != cudaSuccess) {
-    if (d) cudaFree(d);
-    return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
+  cudaError_t e;
+  if (on_stream) {
+    // stream-ordered: pooled device blob, pooled pinned staging, one async copy
+    // queued on the caller's stream; nothing here waits for the device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PoolBlock host;
+    e = device_pool().acquire(stage.size() + 16, dev, &b->dev_block);
+    if (e == cudaSuccess) e = pinned_pool().acquire(stage.size() + 16, dev, &host);
+    if (e == cudaSuccess) {
+      b->pooled = true;
+      b->streams.push_back(stream);
+      d = static_cast<unsigned char *>(b->dev_block.p);
+      std::memcpy(host.p, stage.data(), stage.size());
+      if (!stage.empty()) e = cudaMemcpyAsync(d, host.p, stage.size(), cudaMemcpyHostToDevice, stream);
+      cudaEvent_t ev = nullptr;
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventRecord(ev, stream);
+      if (e != cudaSuccess) cudaStreamSynchronize(stream);       // staging must not be reused early
+      if (ev && e == cudaSuccess) host.pending.push_back(ev);
+      else if (ev) cudaEventDestroy(ev);
+      pinned_pool().release(host);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
+    }
+  } else {
+    e = cudaMalloc(&d, stage.size() + 16);
+    if (e == cudaSuccess) e = upload(d, stage.data(), stage.size());
+    if (e != cudaSuccess) {
+      if (d) cudaFree(d);
+      return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
+    }
   }
   b->d_blob = d;
   b->d_sample_begin = reinterpret_cast<int64_t *>(d + o_begin);
@@ -1244,7 +1290,31 @@ extern "C" int snb_batch_create(const snb_plan *plan, const int64_t *sample_begi
 
 extern "C" void snb_batch_destroy(snb_batch *b) {
   if (!b) return;
-  if (b->d_blob) cudaFree(b->d_blob);
+  if (b->pooled) {
+    // recycle the blob once everything queued so far on the streams that used
+    // the batch has drained; an unrecordable stream falls back to cudaFree
+    bool ok = true;
+    for (cudaStream_t s : b->streams) {
+      cudaEvent_t ev = nullptr;
+      cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventRecord(ev, s);
+      if (e != cudaSuccess) {
+        if (ev) cudaEventDestroy(ev);
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      b->dev_block.pending.push_back(ev);
+    }
+    if (ok) {
+      device_pool().release(b->dev_block);
+    } else {
+      for (cudaEvent_t ev : b->dev_block.pending) cudaEventDestroy(ev);
+      if (b->dev_block.p) cudaFree(b->dev_block.p);
+    }
+  } else if (b->d_blob) {
+    cudaFree(b->d_blob);
+  }
   delete b;
 }
 extern "C" int64_t snb_batch_num_utts(const snb_batch *b) { return b->nutts; }
@@ -1295,6 +1365,7 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
   const FeatParams &p = plan->params;
   if (ld_out < p.dim) return set_error(SNB_ERR_VALUE, "ld_out %lld < dim %d", (long long)ld_out, p.dim);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  batch->note_stream(stream);
   if (plan->fast_path && !d_wave) {
     FastArgs a;
     a.p = p;

@@ -1153,6 +1153,7 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
     return set_error(SNB_ERR_VALUE, "pitch workspace too small");
   const PitchTables *t = plan->pitch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  batch->note_stream(stream);
   const bool warp_path = use_warp_tracker(t);
   int warp_grid = 1, warp_count = kTrackWarpsMin;
   const int64_t grid = warp_path ? pitch_slots(t, batch->nutts, &warp_grid, &warp_count)

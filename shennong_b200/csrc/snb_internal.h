@@ -137,8 +137,49 @@ struct snb_plan {
   snb::PitchTables *pitch = nullptr;
 };
 
+namespace snb {
+// A block of device (or pinned host) memory on loan from a MemPool; `pending`
+// are the events that must complete before the block may be handed out again
+struct PoolBlock {
+  void *p = nullptr;
+  size_t cap = 0;
+  int device = 0;
+  std::vector<cudaEvent_t> pending;
+};
+
+// Recycles the small per-batch allocations so that the steady state of a
+// chunked pipeline performs no cudaMalloc / cudaFree / cudaHostAlloc (cudaFree
+// synchronises the whole device).  Thread-safe.
+class MemPool {
+ public:
+  explicit MemPool(bool pinned) : pinned_(pinned) {}
+  cudaError_t acquire(size_t bytes, int device, PoolBlock *out);
+  void release(PoolBlock block);       // takes ownership of block.pending
+ private:
+  static bool ready(PoolBlock *b);
+  void free_block(PoolBlock *b);
+  bool pinned_;
+  std::mutex mu_;
+  std::vector<PoolBlock> free_;
+};
+MemPool &device_pool();
+MemPool &pinned_pool();
+}  // namespace snb
+
 struct snb_batch {
   const snb_plan *plan;
+  // stream-ordered batches (snb_batch_create_on_stream): pooled blob, and the
+  // streams whose queued work must drain before the blob is recycled
+  bool pooled = false;
+  snb::PoolBlock dev_block;
+  mutable std::mutex stream_mu;
+  mutable std::vector<cudaStream_t> streams;
+  void note_stream(cudaStream_t s) const {
+    if (!pooled) return;
+    std::lock_guard<std::mutex> lock(stream_mu);
+    for (cudaStream_t t : streams) if (t == s) return;
+    streams.push_back(s);
+  }
   int64_t nutts = 0, total_frames = 0, total_samples = 0;
   std::vector<int64_t> sample_begin, sample_len, frame_offsets;
   void *d_blob = nullptr;            // single device allocation; the pointers below alias it

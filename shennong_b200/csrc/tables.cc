@@ -4,6 +4,7 @@
 // shennong (frames.py:137, window.py:107-114, processor/base.py:308,
 // processor/plp.py:468-506); float32 storage with double intermediates
 // exactly where Kaldi has them.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -41,6 +42,80 @@ cudaError_t upload(void *dst, const void *src, size_t bytes) {
   if (e != cudaSuccess) return e;
   return cudaStreamSynchronize(stream);
 }
+
+// ---- MemPool ----------------------------------------------------------------
+bool MemPool::ready(PoolBlock *b) {
+  for (cudaEvent_t ev : b->pending) {
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e == cudaErrorNotReady) {
+      cudaGetLastError();
+      return false;
+    }
+    if (e != cudaSuccess) cudaGetLastError();     // broken event: nothing can still be queued on it
+  }
+  for (cudaEvent_t ev : b->pending) cudaEventDestroy(ev);
+  b->pending.clear();
+  return true;
+}
+
+void MemPool::free_block(PoolBlock *b) {
+  for (cudaEvent_t ev : b->pending) {
+    cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+  }
+  b->pending.clear();
+  if (b->p) {
+    if (pinned_) cudaFreeHost(b->p); else cudaFree(b->p);
+  }
+  cudaGetLastError();
+  b->p = nullptr;
+}
+
+cudaError_t MemPool::acquire(size_t bytes, int device, PoolBlock *out) {
+  const size_t want = std::max<size_t>(bytes, 1);
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    int best = -1;
+    for (size_t i = 0; i < free_.size(); ++i) {
+      PoolBlock &b = free_[i];
+      if (b.device != device || b.cap < want || b.cap > std::max<size_t>(4 * want, 1 << 20)) continue;
+      if (best >= 0 && free_[best].cap <= b.cap) continue;
+      if (!ready(&b)) continue;
+      best = static_cast<int>(i);
+    }
+    if (best >= 0) {
+      *out = free_[best];
+      free_.erase(free_.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  PoolBlock b;
+  b.device = device;
+  b.cap = (want + 65535) / 65536 * 65536;
+  const cudaError_t e = pinned_ ? cudaHostAlloc(&b.p, b.cap, cudaHostAllocDefault) : cudaMalloc(&b.p, b.cap);
+  if (e != cudaSuccess) return e;
+  *out = b;
+  return cudaSuccess;
+}
+
+void MemPool::release(PoolBlock block) {
+  if (!block.p) return;
+  constexpr size_t kMaxFree = 64;
+  std::lock_guard<std::mutex> lock(mu_);
+  free_.push_back(block);
+  if (free_.size() > kMaxFree) {                  // trim: oldest block whose work has drained
+    for (size_t i = 0; i < free_.size(); ++i) {
+      if (ready(&free_[i])) {
+        free_block(&free_[i]);
+        free_.erase(free_.begin() + i);
+        break;
+      }
+    }
+  }
+}
+
+MemPool &device_pool() { static MemPool *p = new MemPool(false); return *p; }
+MemPool &pinned_pool() { static MemPool *p = new MemPool(true); return *p; }
 
 int32_t window_shift(const snb_frame_opts &o) {
   return static_cast<int32_t>(static_cast<double>(o.samp_freq) * 0.001 *

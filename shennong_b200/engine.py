@@ -168,11 +168,14 @@ class Batch:
             if warps.shape != (nutts,):
                 raise ValueError('one vtln warp per utterance is expected')
         handle = ctypes.c_void_p()
-        _lib.check(L.snb_batch_create(
+        # stream-ordered creation: the descriptor upload is queued on the
+        # current stream (where the kernels that read it are launched) and
+        # the device blob is recycled through the library's pool
+        _lib.check(L.snb_batch_create_on_stream(
             plan.handle, _lib.np_ptr(packed.starts),
             _lib.np_ptr(packed.lengths), nutts,
             _lib.np_ptr(warps) if warps is not None else None,
-            ctypes.byref(handle)))
+            _stream_ptr(), ctypes.byref(handle)))
         self.handle = handle
         self.nutts = nutts
         self.total_frames = int(L.snb_batch_total_frames(handle))

@@ -71,18 +71,22 @@ class FusedPipeline:
         return plans
 
     def run_device(self, packed, speakers=None, warps=None, seed=None,
-                   out=None, plans=None):
+                   out=None, plans=None, base_buf=None, batch=None):
         """Runs the whole pipeline on a PackedAudio already on the device
 
         Returns (out [total_frames, out_dim] device tensor, frame_offsets
         int64 [U+1] host array, stats float64 device tensor or None,
         group index of each utterance or None).  All launches are queued on
-        the current stream; nothing synchronises.
+        the current stream; nothing synchronises.  `base_buf` is an optional
+        preallocated [>= total_frames, base_dim] float32 buffer for the
+        intermediate base features (chunked pipelines reuse it); `batch` an
+        engine.Batch of the features plan already created for `packed`.
         """
         torch = engine.require_cuda()
         plans = plans or self._plans()
         p = self.processor
-        batch = engine.Batch(plans['feat'], packed, warps)
+        if batch is None:
+            batch = engine.Batch(plans['feat'], packed, warps)
         layout = engine.RowLayout(batch=batch)
         if seed is None:
             seed = engine.next_seed() if p.dither != 0 else 0
@@ -95,7 +99,9 @@ class FusedPipeline:
             base = out[:, :self.base_dim]
             engine.compute_features(plans['feat'], batch, seed=seed, out=base)
         else:
-            base = engine.compute_features(plans['feat'], batch, seed=seed)
+            base = engine.compute_features(
+                plans['feat'], batch, seed=seed,
+                out=None if base_buf is None else base_buf[:total])
         stats, utt_group, norm = None, None, None
         if self.cmvn is not None:
             weights = None
@@ -192,10 +198,14 @@ class FusedPipeline:
                         for _ in range(nslots)],
                 'out': [torch.empty((max_rows, self.out_dim),
                                     dtype=torch.float32, device='cuda')
-                        for _ in range(nslots)]}
+                        for _ in range(nslots)],
+                'base': [torch.empty((max_rows, self.base_dim),
+                                     dtype=torch.float32, device='cuda')
+                         for _ in range(nslots)]}
             self._host_state = state
         s_in, s_c, s_out = state['streams']
         pcm_slots, out_slots = state['pcm'], state['out']
+        base_slots = state['base']
         for s in (s_in, s_c, s_out):      # order after the caller's stream
             s.wait_stream(torch.cuda.current_stream())
         free_ev = [None] * nslots        # D2H of the slot's previous use
@@ -205,6 +215,13 @@ class FusedPipeline:
             begin = int(starts[b])
             n = int(starts[e - 1] + lengths[e - 1]) - begin
             with torch.cuda.stream(s_in):
+                # the (small) batch descriptor goes first: queued behind the
+                # PCM copies of later chunks it would hold back this chunk's
+                # kernels and drain the slot ring
+                packed = engine.PackedAudio.from_packed(
+                    None, starts[b:e] - begin, lengths[b:e],
+                    dev=pcm_slots[slot])
+                batch = engine.Batch(plans['feat'], packed)
                 if free_ev[slot] is not None:
                     s_in.wait_event(free_ev[slot])
                 pcm_slots[slot][:n].copy_(
@@ -214,11 +231,9 @@ class FusedPipeline:
             rows = int(foffs[e] - foffs[b])
             with torch.cuda.stream(s_c):
                 s_c.wait_event(ev_in)
-                packed = engine.PackedAudio.from_packed(
-                    None, starts[b:e] - begin, lengths[b:e],
-                    dev=pcm_slots[slot])
                 out_dev = out_slots[slot][:rows]
-                self.run_device(packed, out=out_dev, plans=plans)
+                self.run_device(packed, out=out_dev, plans=plans,
+                                base_buf=base_slots[slot], batch=batch)
                 keep.append((packed, self._last))
                 ev_c = torch.cuda.Event()
                 ev_c.record(s_c)

@@ -116,3 +116,32 @@ def test_run_host_chunked_streams(signals, chunk):
     out2, _ = pipe.run_host(
         packed.host, packed.starts, packed.lengths, chunk_utts=chunk)
     assert np.array_equal(out2.numpy(), ref)
+
+
+def test_stream_ordered_batches_recycle_safely(signals):
+    """Batches are created on the current stream and their device blob is
+    recycled through the library's pool: destroying a batch right after
+    queueing the kernels that read it (here on a side stream, many times,
+    with changing shapes) must never corrupt a launch still in flight"""
+    import torch
+    proc = MfccProcessor(dither=0)
+    plan = engine.feature_plan(
+        proc._frame_opts(), proc._mel_opts(), proc._feat_opts())
+    subsets = [signals[:k] for k in (9, 3, 5, 1, 7, 2)]
+    packs = [engine.PackedAudio(s) for s in subsets]
+    refs = []
+    for p in packs:
+        refs.append(engine.to_host(
+            engine.compute_features(plan, engine.Batch(plan, p))))
+    side = torch.cuda.Stream()
+    outs = []
+    with torch.cuda.stream(side):
+        for rep in range(40):
+            p = packs[rep % len(packs)]
+            batch = engine.Batch(plan, p)
+            outs.append((rep % len(packs),
+                         engine.compute_features(plan, batch)))
+            del batch            # blob goes back to the pool, kernel queued
+    side.synchronize()
+    for k, out in outs:
+        assert np.array_equal(engine.to_host(out), refs[k])

@@ -91,6 +91,8 @@ def main():
     ap.add_argument('source')
     ap.add_argument('--so', default='shennong_b200/_build/libsnb.so')
     ap.add_argument('--top', type=int, default=30)
+    ap.add_argument('--sass', default=None,
+                    help='regex on the mangled name (template instances)')
     a = ap.parse_args()
 
     raw = ncu_page(a.report, 'raw')
@@ -110,7 +112,7 @@ def main():
     hdr = [i for i, r in enumerate(src) if 'Instructions Executed' in r][0]
     cols, data = src[hdr], src[hdr + 1:]
     ie, isamp = cols.index('Instructions Executed'), cols.index('# Samples')
-    seq = sass_lines(a.so, a.source, a.kernel)
+    seq = sass_lines(a.so, a.source, a.sass or a.kernel)
     print(f'\n# source page: {len(data)} SASS instructions in the report, '
           f'{len(seq)} in the listing of {a.so}')
     if len(seq) != len(data):
