@@ -1,17 +1,14 @@
 """A dict of Features indexed by utterance name
 
-Counterpart of shennong/features_collection.py.  Serialisation supports the
-formats that need no third party backend here: pickle (.pkl) and numpy
-(.npz); the other formats of the reference (h5features, matlab, kaldi ark,
-csv) are "next" rows of the scope table.
+Counterpart of shennong/features_collection.py; the file formats live in
+shennong_b200/serializers.py.
 """
-
-import os
-import pickle
 
 import numpy as np
 
 from shennong_b200.features import Features
+from shennong_b200.logger import get_logger
+from shennong_b200.serializers import get_serializer
 
 
 class FeaturesCollection(dict):
@@ -57,47 +54,21 @@ class FeaturesCollection(dict):
                 properties=feats.properties)
         return out
 
-    @staticmethod
-    def _format(filename, serializer):
-        if serializer is None:
-            ext = os.path.splitext(filename)[1]
-            serializer = {'.pkl': 'pickle', '.npz': 'numpy'}.get(ext)
-            if serializer is None:
-                raise ValueError(
-                    f'invalid extension {ext} of file {filename}, must be '
-                    f'.pkl or .npz (other formats are not implemented)')
-        if serializer not in ('pickle', 'numpy'):
-            raise ValueError(
-                f'invalid serializer {serializer}, must be pickle or numpy')
-        return serializer
+    def save(self, filename, serializer=None, with_properties=True,
+             log=get_logger('features', 'warning'), **kwargs):
+        """Saves the collection to `filename`
 
-    def save(self, filename, serializer=None, with_properties=True):
-        """Saves the collection to `filename` (.pkl or .npz)"""
-        filename = str(filename)
-        serializer = self._format(filename, serializer)
-        if os.path.exists(filename):
-            raise IOError(f'file already exists: {filename}')
-        if serializer == 'pickle':
-            with open(filename, 'wb') as stream:
-                pickle.dump(
-                    {k: v._to_dict(with_properties) for k, v in self.items()},
-                    stream, protocol=4)
-        else:
-            np.savez_compressed(filename, features=np.asarray(
-                {k: v._to_dict(with_properties) for k, v in self.items()},
-                dtype=object))
+        The format is guessed from the extension (.npz, .pkl, .mat, .ark,
+        .h5f, or a directory name for csv) unless `serializer` names it
+        (see serializers.supported_serializers).  `kwargs` are specific to
+        the format (e.g. ``scp=True`` for kaldi, ``compress``).
+        Raises IOError if the file exists, ValueError on invalid format.
+        """
+        get_serializer(self.__class__, str(filename), log, serializer).save(
+            self, with_properties=with_properties, **kwargs)
 
     @classmethod
-    def load(cls, filename, serializer=None):
+    def load(cls, filename, serializer=None,
+             log=get_logger('features', 'warning')):
         """Loads a collection saved with :meth:`save`"""
-        filename = str(filename)
-        serializer = cls._format(filename, serializer)
-        if not os.path.isfile(filename):
-            raise IOError(f'file not found: {filename}')
-        if serializer == 'pickle':
-            with open(filename, 'rb') as stream:
-                raw = pickle.load(stream)
-        else:
-            raw = np.load(filename, allow_pickle=True)['features'].item()
-        return cls({k: Features._from_dict(v, validate=False)
-                    for k, v in raw.items()})
+        return get_serializer(cls, str(filename), log, serializer).load()

@@ -282,6 +282,86 @@ def extract_features(configuration, utterances, warps=None, njobs=1,
     return FeaturesCollection((u.name, out[u.name]) for u in utts)
 
 
+def _warp_setup(configuration, utterances, njobs, log):
+    """Shared front end of the warp extractions: (manager, utts, audios)"""
+    njobs = get_njobs(njobs, log=log)
+    config = _init_config(configuration, log=log)
+    manager = PipelineManager(config, utterances, log=log)
+    utts = list(utterances)
+    if njobs > 1 and len(utts) > 1:
+        with concurrent.futures.ThreadPoolExecutor(njobs) as pool:
+            audios = list(pool.map(manager.get_audio, utts))
+    else:
+        audios = [manager.get_audio(u) for u in utts]
+    for audio in audios:
+        if audio.nchannels != 1:
+            raise ValueError(
+                'signal must have one dimension, but it has {}'.format(
+                    audio.nchannels))
+    return manager, utts, audios
+
+
+def extract_features_warp(configuration, utterances, warp,
+                          log=get_logger('pipeline', 'warning'), njobs=1):
+    """Features extraction when all features are warped by the same factor
+
+    Mirrors shennong/pipeline.py:669-696 (used by VTLN training): main
+    features with ``vtln_warp=warp`` then deltas -- no CMVN, no pitch.
+    """
+    return extract_features_warp_sweep(
+        configuration, utterances, [warp], log=log, njobs=njobs)[float(warp)]
+
+
+def extract_features_warp_sweep(configuration, utterances, warps,
+                                log=get_logger('pipeline', 'warning'),
+                                njobs=1):
+    """`extract_features_warp` for a whole grid of warps in ONE fused batch
+
+    The VTLN trainer of the reference re-extracts every utterance for every
+    warp of its grid (processor/vtln.py:580-622), i.e. calls
+    ``extract_features_warp`` ~21 times.  Here the PCM is packed and uploaded
+    once and the grid becomes ``len(warps) x len(utterances)`` virtual
+    utterances of one batch (same sample ranges, one mel table per warp).
+
+    Returns a dict {warp: FeaturesCollection}.
+    """
+    warps = [float(w) for w in warps]
+    manager, utts, audios = _warp_setup(configuration, utterances, njobs, log)
+    if manager.features == 'spectrogram':
+        raise ValueError('spectrogram features cannot be warped')
+    out = {w: {} for w in warps}
+    rates = sorted(set(a.sample_rate for a in audios))
+    for rate in rates:
+        idx = [i for i, a in enumerate(audios) if a.sample_rate == rate]
+        gutts = [utts[i] for i in idx]
+        proc = manager.get_features_processor(gutts[0])
+        delta = (manager.get_delta_processor()
+                 if 'delta' in manager.config else None)
+        packed = engine.PackedAudio(
+            [audios[i].astype(np.int16).data for i in idx])
+        nutt, nwarp = len(idx), len(warps)
+        virtual = engine.PackedAudio.from_packed(
+            None, np.tile(packed.starts, nwarp),
+            np.tile(packed.lengths, nwarp), dev=packed.dev)
+        pipe = FusedPipeline(proc, delta=delta)
+        dev, offs, _, _ = pipe.run_device(
+            virtual, warps=np.repeat(np.asarray(warps, np.float32), nutt))
+        data = engine.to_host(dev)
+        for k, warp in enumerate(warps):
+            for j, utt in enumerate(gutts):
+                row = k * nutt + j
+                block = data[offs[row]:offs[row + 1]]
+                carrier = _Carrier(
+                    proc.get_properties(vtln_warp=warp), proc.ndims)
+                if delta is not None:
+                    carrier = _Carrier(delta.get_properties(carrier),
+                                       proc.ndims * (delta.order + 1))
+                out[warp][utt.name] = Features(
+                    block, proc.times(block.shape[0]), carrier.properties)
+    return {w: FeaturesCollection((u.name, out[w][u.name]) for u in utts)
+            for w in warps}
+
+
 def _extract_group(manager, utts, audios, log):
     config = manager.config
     proc = manager.get_features_processor(utts[0])

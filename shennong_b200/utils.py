@@ -49,3 +49,25 @@ def list2array(obj):
 def dict_equal(dict1, dict2):
     """Equality of dicts that may hold numpy arrays (shennong/utils.py:78-96)"""
     return array2list(dict1) == array2list(dict2)
+
+
+def list_files_with_extension(directory, extension, abspath=False,
+                              realpath=True, recursive=True):
+    """Sorted list of the files of `directory` whose name ends with
+    `extension` (shennong/utils.py:99-147): paths relative to `directory`
+    unless `abspath` or `realpath`; `recursive` walks the subdirectories"""
+    import os
+    found = []
+    for root, _, names in os.walk(directory):
+        for name in names:
+            if name.endswith(extension):
+                found.append(os.path.join(root, name))
+        if not recursive:
+            break
+    if abspath:
+        found = [os.path.abspath(f) for f in found]
+    if realpath:
+        found = [os.path.realpath(f) for f in found]
+    if not (abspath or realpath):
+        found = [os.path.relpath(f, directory) for f in found]
+    return sorted(found)

@@ -164,3 +164,36 @@ def test_errors(corpus):
     config = pipeline.get_default_config('mfcc', with_cmvn=True)
     with pytest.raises(ValueError, match='no speaker information'):
         pipeline.extract_features(config, Utterances([e[:2] for e in corpus[:2]]))
+
+
+def test_extract_features_warp_and_sweep(corpus):
+    """extract_features_warp (pipeline.py:669-696 of the reference: main
+    features with one warp, then deltas, no CMVN) and its batched sweep over
+    a grid of warps: equal to the per-utterance processors, bit-identical
+    between the single-warp and the sweep forms"""
+    config = no_dither(pipeline.get_default_config('mfcc', with_delta=True))
+    utts = Utterances(corpus[:3])
+    grid = [0.85, 1.0, 1.2]
+    sweep = pipeline.extract_features_warp_sweep(config, utts, grid)
+    assert sorted(sweep) == grid
+    proc = MfccProcessor(**config['mfcc'])
+    for warp in grid:
+        single = pipeline.extract_features_warp(config, utts, warp)
+        assert list(single.keys()) == ['utt0', 'utt1', 'utt2']
+        for name, path, _ in corpus[:3]:
+            ref = DeltaPostProcessor().process(
+                proc.process(Audio.load(path), vtln_warp=warp))
+            got = single[name]
+            assert got.shape == ref.shape
+            assert np.array_equal(got.times, ref.times)
+            assert np.allclose(got.data, ref.data, rtol=1e-5, atol=1e-5)
+            assert got.properties['mfcc']['vtln_warp'] == warp
+            assert np.array_equal(sweep[warp][name].data, got.data)
+    # warping changes the features, the identity warp does not
+    base = pipeline.extract_features(config, utts)
+    assert np.array_equal(sweep[1.0]['utt0'].data, base['utt0'].data)
+    assert not np.allclose(sweep[0.85]['utt0'].data, base['utt0'].data)
+    with pytest.raises(ValueError):
+        pipeline.extract_features_warp(
+            no_dither(pipeline.get_default_config(
+                'spectrogram', with_cmvn=False)), utts, 1.1)
