@@ -39,6 +39,11 @@ SAMPLE_RATE = 16000
 UTT_SAMPLES = 160000            # 10 s
 FRAMES_PER_UTT = 998
 BYTES_PER_FRAME_KERNEL = 320 + 4 * 13     # PCM read once + 13 cepstra written
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_features_512_kernel
+# launch over 9.98e6 frames (ncu capture of `bench.py --steps 2 --warmup 2`,
+# profiles/r01_ncu_traffic_fused_features_512_final.csv): 3 217 049 088 +
+# 509 941 760 B = 373.4 B/frame, i.e. 1.003 x the algorithmic bytes
+NCU_TRAFFIC_BYTES_PER_FRAME = (3217049088 + 509941760) / 9980000.0
 BYTES_PER_FRAME_PIPELINE = 320 + 4 * 39   # + delta/cmvn output
 FLOPS_PER_FRAME = 17000
 
@@ -364,7 +369,11 @@ def main():
     roofline = {
         'bound': 'hbm', 'kernel': 'fused_features_512_kernel',
         'achieved': feat_gbs, 'peak': peak, 'unit': 'GB/s',
-        'frac': feat_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+        'frac': feat_gbs / peak,
+        'traffic': int(total_frames * NCU_TRAFFIC_BYTES_PER_FRAME),
+        'traffic_source': 'ncu capture of this launch shape, '
+                          'profiles/r01_ncu_traffic_fused_features_512_final.csv',
+        'peak_source': peak_src,
         'algorithmic_bytes_per_launch': int(total_frames * BYTES_PER_FRAME_KERNEL),
         'kernel_ms': ms_feat,
         'note': ('the chain is fp32/SFU-bound (~17 kflop/frame, AI ~45 flop/B): '
