@@ -65,6 +65,7 @@ __device__ __forceinline__ MelView mel_view(const int32_t *blob, const FeatParam
 
 struct TailTables {       // tables the tails read (shared memory in both paths)
   const float *dct, *lifter, *idft;
+  int dct_stride;         // floats between DCT rows (fast path: padded, see fast_layout)
   MelView mel;
 };
 
@@ -222,13 +223,26 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
       out_row[xo.htk_compat ? B : 0] = log_energy;
     return;
   }
-  __syncwarp();
   const int nc = xo.num_ceps;
+  if (G == 16 && xo.kind == SNB_FEAT_MFCC && B + gl < ((B + 3) & ~3)) mel[B + gl] = 0.0f;
+  __syncwarp();
   if (xo.kind == SNB_FEAT_MFCC) {
     for (int c = gl; c < nc; c += G) {
-      const float *row = t.dct + c * B;
+      const float *row = t.dct + c * t.dct_stride;
       float acc = 0.0f;
-      for (int n = 0; n < B; ++n) acc = fmaf(row[n], mel[n], acc);
+      if (G == 16) {
+        // rows and mel[] are zero padded to a multiple of four: 128-bit loads,
+        // same summation order as the scalar loop (the padding adds +0 terms)
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        const float4 *mel4 = reinterpret_cast<const float4 *>(mel);
+        for (int n4 = 0; n4 < (B + 3) / 4; ++n4) {
+          const float4 r = row4[n4], m = mel4[n4];
+          acc = fmaf(r.x, m.x, acc); acc = fmaf(r.y, m.y, acc);
+          acc = fmaf(r.z, m.z, acc); acc = fmaf(r.w, m.w, acc);
+        }
+      } else {
+        for (int n = 0; n < B; ++n) acc = fmaf(row[n], mel[n], acc);
+      }
       if (xo.cepstral_lifter != 0.0f) acc *= t.lifter[c];
       if (c == 0 && xo.use_energy) acc = log_energy;
       int col = c;
@@ -265,8 +279,17 @@ constexpr int kXStride = 17;            // float2 row stride of the transpose bu
 
 struct FastSmemLayout {                 // byte offsets into dynamic smem
   int window, tw1, tw2, dct, lifter, idft, mel, pcm, grp, bar, total;
-  int grp_floats, span_cap;
+  int grp_floats, span_cap, dct_stride;
 };
+
+// two int16 samples packed in one 32-bit word -> two floats without the
+// quarter-rate I2F: splice each half (biased by 0x8000) into the mantissa of
+// 2^23 and subtract 2^23 + 2^15; exact for every int16 value
+__device__ __forceinline__ void s16x2_to_f32(uint32_t pr, float *v0, float *v1) {
+  const uint32_t u = pr ^ 0x80008000u;
+  *v0 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7410)) - 8421376.0f;
+  *v1 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7432)) - 8421376.0f;
+}
 
 struct FastArgs {
   FeatParams p;
@@ -287,8 +310,12 @@ struct FastArgs {
 
 // kMinBlocks = 3: 80 registers; kMinBlocks = 4: 64 registers (no spills), 32
 // resident warps per SM -- selected at plan time when the shared memory of four
-// CTAs fits (SNB_FUSED_OCC=3|4 overrides)
-template <int kMinBlocks>
+// CTAs fits (SNB_FUSED_OCC=3|4 overrides).
+// kW > 0: the window length is a compile-time constant (400 = 25 ms at 16 kHz,
+// every BASELINE configuration): the per-element "is this sample inside the
+// window" tests of the unrolled stages fold away and the stages stop at the
+// last register that can hold a sample.  kW = 0: any window of 257..512.
+template <int kMinBlocks, int kW>
 __global__ void __launch_bounds__(kFastThreads, kMinBlocks)
 fused_features_512_kernel(const FastArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -312,7 +339,9 @@ fused_features_512_kernel(const FastArgs a) {
   float *s_grp = s_grp_all + grp * a.sm.grp_floats;
   float2 *s_x = reinterpret_cast<float2 *>(s_grp);
 
-  const int W = p.W, S = p.S, B = p.B;
+  const int W = (kW > 0) ? kW : p.W;
+  const int S = p.S, B = p.B;
+  constexpr int kN1 = (kW > 0) ? (kW + 31) / 32 : 16;   // registers that can hold samples
   const snb_feat_opts &xo = p.xo;
   const int kind = xo.kind;
 
@@ -324,7 +353,10 @@ fused_features_512_kernel(const FastArgs a) {
     if (i < 128) s_tw2[i] = p.t.tw_full[l + 16 * k1];   // k2 = k1 < 8
   }
   if (kind == SNB_FEAT_MFCC)
-    for (int i = tid; i < xo.num_ceps * B; i += kFastThreads) s_dct[i] = p.t.dct[i];
+    for (int i = tid; i < xo.num_ceps * a.sm.dct_stride; i += kFastThreads) {
+      const int c = i / a.sm.dct_stride, n = i - c * a.sm.dct_stride;
+      s_dct[i] = (n < B) ? p.t.dct[c * B + n] : 0.0f;
+    }
   if (kind == SNB_FEAT_MFCC || kind == SNB_FEAT_PLP)
     for (int i = tid; i < xo.num_ceps; i += kFastThreads) s_lifter[i] = p.t.lifter[i];
   if (kind == SNB_FEAT_PLP)
@@ -337,6 +369,7 @@ fused_features_512_kernel(const FastArgs a) {
   uint32_t parity = 0;
   TailTables tt;
   tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
+  tt.dct_stride = a.sm.dct_stride;
   tt.mel = mel_view(s_mel, p);
 
   const bool pair_ok_static = (S % 2) == 0;
@@ -421,11 +454,11 @@ fused_features_512_kernel(const FastArgs a) {
       for (int n1 = 0; n1 < 16; ++n1) {
         const int i0 = 2 * (16 * n1 + hl);
         float v0 = 0.0f, v1 = 0.0f;
-        if (n1 < nfull) {
+        if (n1 >= kN1) {
+          // statically beyond the window: zero padding of the FFT
+        } else if (n1 < nfull) {
           if (pair_ok) {
-            const int32_t pr = *reinterpret_cast<const int32_t *>(fr + i0);
-            v0 = static_cast<float>(static_cast<int16_t>(pr & 0xffff));
-            v1 = static_cast<float>(pr >> 16);
+            s16x2_to_f32(*reinterpret_cast<const uint32_t *>(fr + i0), &v0, &v1);
           } else {
             v0 = static_cast<float>(fr[i0]);
             v1 = static_cast<float>(fr[i0 + 1]);
@@ -450,7 +483,7 @@ fused_features_512_kernel(const FastArgs a) {
       if (p.fo.remove_dc_offset) {
         const float mean = __fdiv_rn(group_sum<16>(lsum), static_cast<float>(W));
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
+        for (int n1 = 0; n1 < kN1; ++n1) {
           if (n1 < nfull) {
             xr[n1] -= mean; xi[n1] -= mean;
           } else if (n1 == nfull) {
@@ -465,7 +498,7 @@ fused_features_512_kernel(const FastArgs a) {
       if (p.need_raw_energy) {
         float e = 0.0f;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
+        for (int n1 = 0; n1 < kN1; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
         e = group_sum<16>(e);
         log_energy = logf(fmaxf(e, p.eps_energy));
       }
@@ -473,7 +506,7 @@ fused_features_512_kernel(const FastArgs a) {
       if (p.fo.preemph_coeff != 0.0f) {
         const float c = p.fo.preemph_coeff;
 #pragma unroll
-        for (int n1 = 15; n1 >= 0; --n1) {
+        for (int n1 = kN1 - 1; n1 >= 0; --n1) {
           const float send = (hl == 15) ? xi[(n1 + 15) & 15] : xi[n1];
           float prev = __shfl_sync(SNB_FULL_MASK, send, gbase | ((hl + 15) & 15));
           if (n1 == 0 && hl == 0) prev = xr[0];
@@ -483,14 +516,14 @@ fused_features_512_kernel(const FastArgs a) {
       }
       // ---- window (zero beyond W: also clears pre-emphasis spill) ----
 #pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) {
+      for (int n1 = 0; n1 < kN1; ++n1) {
         const float2 w = *reinterpret_cast<const float2 *>(s_window + 2 * (16 * n1 + hl));
         xr[n1] *= w.x; xi[n1] *= w.y;
       }
       if (kind == SNB_FEAT_ENERGY) {
         double e = 0.0;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1)
+        for (int n1 = 0; n1 < kN1; ++n1)
           e += static_cast<double>(xr[n1]) * xr[n1] + static_cast<double>(xi[n1]) * xi[n1];
         e = group_sum_f64<16>(e);
         if (valid && hl == 0)
@@ -501,7 +534,7 @@ fused_features_512_kernel(const FastArgs a) {
       if (p.need_post_energy) {
         float e = 0.0f;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
+        for (int n1 = 0; n1 < kN1; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
         e = group_sum<16>(e);
         log_energy = logf(fmaxf(e, p.eps_energy));
       }
@@ -622,6 +655,7 @@ generic_features_kernel(const GenArgs a) {
 
   TailTables tt;
   tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
+  tt.dct_stride = B;
 
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kGenWarps + warp; row < a.total_frames;
        row += static_cast<int64_t>(gridDim.x) * kGenWarps) {
@@ -798,6 +832,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) plp_from_mel_kernel(const PlpM
   float *scratch = s_tables + a.tables_floats + static_cast<int64_t>(warp) * a.warp_floats;
   TailTables tt;
   tt.dct = nullptr; tt.lifter = s_lifter; tt.idft = s_idft;
+  tt.dct_stride = 0;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kGenWarps + warp; row < a.total_frames;
        row += static_cast<int64_t>(gridDim.x) * kGenWarps) {
     const int64_t utt = find_utt(a.frame_offsets, a.nutts, row);
@@ -828,13 +863,20 @@ static void fast_layout(const snb_plan *plan, FastSmemLayout *sm) {
   sm->window = off; off += 512 * 4;
   sm->tw1 = off; off += 256 * 8;
   sm->tw2 = off; off += 128 * 8;
-  sm->dct = off; off += align_up((xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * p.B : 0) * 4, 16);
+  // DCT rows padded to a stride = 4 (mod 8) floats: a quarter warp's 128-bit
+  // row loads then fall in distinct banks
+  sm->dct_stride = align_up(p.B, 4);
+  if (sm->dct_stride % 8 == 0) sm->dct_stride += 4;
+  sm->dct = off; off += align_up((xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * sm->dct_stride : 0) * 4, 16);
   sm->lifter = off; off += align_up(xo.num_ceps * 4, 16);
   sm->idft = off; off += align_up((xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0) * 4, 16);
   sm->mel = off; off += align_up(p.mel_blob_stride * 4, 16);
   sm->span_cap = align_up((plan->tile_frames - 1) * p.S + p.W + 16, 8);
   sm->pcm = off; off += align_up(sm->span_cap * 2, 16);
-  sm->grp_floats = align_up(std::max(16 * kXStride * 2, 272 + (p.B + 2) + (xo.lpc_order + 2) + 2 * (p.B + 2)), 4);
+  // per-group buffers 16 banks apart (size = 16 mod 32 floats): the two
+  // groups of a warp use the same offsets inside their buffers, and with a
+  // multiple of 32 every 32-bit access of the warp was a 2-way bank conflict
+  sm->grp_floats = align_up(std::max(16 * kXStride * 2, 272 + (p.B + 4) + (xo.lpc_order + 2) + 2 * (p.B + 2)), 32) + 16;
   sm->grp = off; off += kFastGroups * sm->grp_floats * 4;
   sm->bar = off; off += 16;
   sm->total = off;
@@ -1339,7 +1381,8 @@ static int ensure_smem(K kernel, size_t bytes, std::atomic<size_t> *current) {
   }
   return SNB_OK;
 }
-static std::atomic<size_t> g_fast_smem{0}, g_fast_smem4{0}, g_gen_smem{0};
+static std::atomic<size_t> g_fast_smem{0}, g_fast_smem4{0}, g_fast_smem_w400{0}, g_fast_smem4_w400{0},
+    g_gen_smem{0};
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -1393,8 +1436,14 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
       kernel<<<static_cast<unsigned>(grid), kFastThreads, a.sm.total, stream>>>(a);
       return SNB_OK;
     };
-    int rc = (plan->fused_occ == 4) ? launch(fused_features_512_kernel<4>, &g_fast_smem4)
-                                    : launch(fused_features_512_kernel<3>, &g_fast_smem);
+    int rc;
+    static const bool no_w400 = getenv("SNB_FUSED_W400") && atoi(getenv("SNB_FUSED_W400")) == 0;
+    if (p.W == 400 && !no_w400)
+      rc = (plan->fused_occ == 4) ? launch(fused_features_512_kernel<4, 400>, &g_fast_smem4_w400)
+                                  : launch(fused_features_512_kernel<3, 400>, &g_fast_smem_w400);
+    else
+      rc = (plan->fused_occ == 4) ? launch(fused_features_512_kernel<4, 0>, &g_fast_smem4)
+                                  : launch(fused_features_512_kernel<3, 0>, &g_fast_smem);
     if (rc != SNB_OK) return rc;
     SNB_LAUNCH_CHECK();
     return SNB_OK;
