@@ -38,36 +38,50 @@ __device__ __forceinline__ int64_t first_sample_of_frame_dev(int64_t frame, cons
 // shared-memory views
 // ---------------------------------------------------------------------------
 struct MelView {          // decoded mel blob (in shared or global memory)
+  const float *loudness;
+  // generic path (per-triangle ranges)
   const int32_t *first, *size, *offset;
-  const float *loudness, *weights;
-  // segment tables (see MelBanksHost): used by the 16-lane fast path
-  const int32_t *seg_first, *seg_size, *lane_seg;
-  const float2 *updown;
-  int nslots;
+  const float *weights;
+  // fused path (see "mel energies" in feature_tail)
+  const float *chunk_w;         // [32][20]: (up, down) of the lane's 8 bins, 4 floats of padding
+  const uint32_t *chunk_meta;   // [32]: bits 0-7 "bin closes a run", bits 8+ first run of the lane
+  const int32_t *run_first;     // [B+2]: first run of every segment
 };
 
 __device__ __forceinline__ MelView mel_view(const int32_t *blob, const FeatParams &p) {
   const int B = p.B;
   MelView v;
-  v.first = blob;
-  v.size = blob + B;
-  v.offset = blob + 2 * B;
-  v.loudness = reinterpret_cast<const float *>(blob + 3 * B);
-  v.weights = reinterpret_cast<const float *>(blob + 4 * B);
-  const int32_t *seg = blob + p.mel_seg_off;
-  v.seg_first = seg;
-  v.seg_size = seg + (B + 1);
-  v.lane_seg = seg + 2 * (B + 1);
-  v.nslots = p.mel_nslots;
-  v.updown = reinterpret_cast<const float2 *>(blob + p.mel_updown_off);
+  v.loudness = reinterpret_cast<const float *>(blob);
+  v.chunk_w = reinterpret_cast<const float *>(blob + p.mel_chunk_off);
+  v.chunk_meta = reinterpret_cast<const uint32_t *>(blob + p.mel_meta_off);
+  v.run_first = blob + p.mel_run_off;
+  v.first = blob + p.mel_gen_off;
+  v.size = v.first + B;
+  v.offset = v.first + 2 * B;
+  v.weights = reinterpret_cast<const float *>(v.first + 3 * B);
   return v;
 }
 
 struct TailTables {       // tables the tails read (shared memory in both paths)
   const float *dct, *lifter, *idft;
   int dct_stride;         // floats between DCT rows (fast path: padded, see fast_layout)
+  // fused path only: the warp's run partials, and the distance between the
+  // buffers of the two lane groups (= frames) of a warp
+  float4 *part;
+  int grp_floats;
   MelView mel;
 };
+
+// Power-spectrum layout.  Generic path: natural order.  Fused path: bin k at
+// (k / 8) * 12 + k % 8, so that a lane reading its 8 consecutive bins with two
+// 128-bit loads (lane stride 12 words) never shares a bank with the other
+// seven lanes of its quarter warp.
+constexpr int kPStride = 12;
+constexpr int kPFloats = 32 * kPStride + 4;      // bins 0..256 (+ padding): scratch starts here
+template <int G>
+__device__ __forceinline__ int pidx(int k) {
+  return (G == 16) ? (k >> 3) * kPStride + (k & 7) : k;
+}
 
 // PLP after the (loudness-weighted, compressed) mel energies are in
 // mel[1..B] = scratch[1..B] (plp.py:590-626): duplicate the ends, IDFT to the
@@ -155,7 +169,7 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
 
   if (xo.kind == SNB_FEAT_SPECTROGRAM) {
     for (int k = gl; k <= half; k += G) {
-      float v = logf(fmaxf(P[k], FLT_EPSILON));
+      float v = logf(fmaxf(P[pidx<G>(k)], FLT_EPSILON));
       if (k == 0) v = log_energy;
       if (valid) out_row[k] = v;
     }
@@ -163,46 +177,57 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
   }
   const int B = p.B;
   if (xo.kind == SNB_FEAT_FBANK && !xo.use_power) {
-    for (int k = gl; k <= half; k += G) P[k] = sqrtf(P[k]);
+    for (int k = gl; k <= half; k += G) P[pidx<G>(k)] = sqrtf(P[pidx<G>(k)]);
     __syncwarp();
   }
   // mel energies
   float *mel = scratch;  // [B+2]; PLP uses mel[1..B] with duplicated ends
   const int moff = (xo.kind == SNB_FEAT_PLP) ? 1 : 0;
-  float *useg = scratch + (B + 2) + (xo.lpc_order + 2);   // [B+1] rising sums
-  float *dseg = useg + (B + 1);                            // [B+1] falling sums
   if (G == 16) {
-    // segment form: every FFT bin is visited once and feeds (up, down) of its
-    // segment; segments are dealt to the lanes by decreasing size (host LPT)
-    for (int slot = 0; slot < t.mel.nslots; ++slot) {
-      const int sgm = t.mel.lane_seg[slot * 16 + gl];
-      if (sgm >= 0) {
-        const int first = t.mel.seg_first[sgm], size = t.mel.seg_size[sgm];
-        const float2 *w = t.mel.updown + first;
-        const float *pp = P + first;
-        float u = 0.0f, d = 0.0f;
-        int i = 0;
-        for (; i + 1 < size; i += 2) {
-          const float2 w0 = w[i], w1 = w[i + 1];
-          const float p0 = pp[i], p1 = pp[i + 1];
-          u = fmaf(w0.x, p0, u); d = fmaf(w0.y, p0, d);
-          u = fmaf(w1.x, p1, u); d = fmaf(w1.y, p1, d);
-        }
-        if (i < size) {
-          const float2 w0 = w[i];
-          const float p0 = pp[i];
-          u = fmaf(w0.x, p0, u); d = fmaf(w0.y, p0, d);
-        }
-        useg[sgm] = u;
-        dseg[sgm] = d;
-      }
+    // Both frames of the warp at once: lane l (0..31) owns the FFT bins
+    // [8 l, 8 l + 8) of the two power spectra.  Every bin belongs to one
+    // segment s (the bins between two consecutive triangle centres) and feeds
+    // the rising side of triangle s (weight up) and the falling side of
+    // triangle s - 1 (weight down).  The lane accumulates (up, down) sums of
+    // both frames along a RUN of bins of one segment, and drops the four sums
+    // into the warp's partial table when the run ends (host-built flags;
+    // runs end at segment and at chunk boundaries).  Weights and spectra come
+    // in with conflict-free 128-bit loads, nothing is read twice.
+    const int lane32 = threadIdx.x & 31;
+    float *P0 = P - (lane32 >> 4) * t.grp_floats;           // spectrum of the warp's first frame
+    const float4 *wv = reinterpret_cast<const float4 *>(t.mel.chunk_w + 20 * lane32);
+    const float4 *pa = reinterpret_cast<const float4 *>(P0 + kPStride * lane32);
+    const float4 *pb = reinterpret_cast<const float4 *>(P0 + t.grp_floats + kPStride * lane32);
+    const uint32_t meta = t.mel.chunk_meta[lane32];
+    float4 *part = t.part + (meta >> 8);
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#define SNB_MEL_BIN(bit, up, dn, xa, xb)                                          \
+    acc.x = fmaf(up, xa, acc.x); acc.y = fmaf(dn, xa, acc.y);                       \
+    acc.z = fmaf(up, xb, acc.z); acc.w = fmaf(dn, xb, acc.w);                       \
+    if (meta & (1u << (bit))) { *part++ = acc; acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 xa = pa[h], xb = pb[h];
+      const float4 w01 = wv[2 * h], w23 = wv[2 * h + 1];
+      SNB_MEL_BIN(4 * h + 0, w01.x, w01.y, xa.x, xb.x)
+      SNB_MEL_BIN(4 * h + 1, w01.z, w01.w, xa.y, xb.y)
+      SNB_MEL_BIN(4 * h + 2, w23.x, w23.y, xa.z, xb.z)
+      SNB_MEL_BIN(4 * h + 3, w23.z, w23.w, xa.w, xb.w)
     }
+#undef SNB_MEL_BIN
     __syncwarp();
   }
   for (int b = gl; b < B; b += G) {
     float acc = 0.0f;
     if (G == 16) {
-      acc = useg[b] + dseg[b + 1];
+      // triangle b = rising sums of segment b + falling sums of segment b + 1,
+      // runs added in bin order (deterministic)
+      const float2 *mine = reinterpret_cast<const float2 *>(t.part) + ((threadIdx.x & 31) >> 4);
+      const int r0 = t.mel.run_first[b], r1 = t.mel.run_first[b + 1], r2 = t.mel.run_first[b + 2];
+      float u = 0.0f, d = 0.0f;
+      for (int j = r0; j < r1; ++j) u += mine[2 * j].x;
+      for (int j = r1; j < r2; ++j) d += mine[2 * j].y;
+      acc = u + d;
     } else {
       const int first = t.mel.first[b], size = t.mel.size[b];
       const float *w = t.mel.weights + t.mel.offset[b];
@@ -278,8 +303,8 @@ constexpr int kFastGroups = 16;         // half-warps per CTA
 constexpr int kXStride = 17;            // float2 row stride of the transpose buffer
 
 struct FastSmemLayout {                 // byte offsets into dynamic smem
-  int window, tw1, tw2, dct, lifter, idft, mel, pcm, grp, bar, total;
-  int grp_floats, span_cap, dct_stride;
+  int window, tw1, tw2, dct, lifter, idft, mel, pcm, grp, part, bar, total;
+  int grp_floats, span_cap, dct_stride, part_floats;
 };
 
 // two int16 samples packed in one 32-bit word -> two floats without the
@@ -371,6 +396,8 @@ fused_features_512_kernel(const FastArgs a) {
   tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
   tt.dct_stride = a.sm.dct_stride;
   tt.mel = mel_view(s_mel, p);
+  tt.part = reinterpret_cast<float4 *>(smem + a.sm.part) + (tid >> 5) * (a.sm.part_floats / 4);
+  tt.grp_floats = a.sm.grp_floats;
 
   const bool pair_ok_static = (S % 2) == 0;
   const float dither = p.fo.dither;
@@ -381,7 +408,7 @@ fused_features_512_kernel(const FastArgs a) {
     __syncthreads();   // previous tile fully consumed (s_pcm, s_mel) + tables visible
     if (B > 0 && td.mel_idx != cur_mel) {
       const int32_t *src = a.mel_blobs + static_cast<int64_t>(td.mel_idx) * p.mel_blob_stride;
-      for (int i = tid; i < p.mel_blob_stride; i += kFastThreads) s_mel[i] = src[i];
+      for (int i = tid; i < p.mel_fast_words; i += kFastThreads) s_mel[i] = src[i];
       cur_mel = td.mel_idx;
     }
     // ---- stage the PCM span of this tile ----
@@ -566,7 +593,10 @@ fused_features_512_kernel(const FastArgs a) {
       __syncwarp();                                   // transpose buffer free -> reuse as P
       float *P = s_grp;
       // ---- real-FFT unpack: pairs (k, 256-k), k = hl + 16 k2, k2 < 8 ----
+      // P in the padded layout of pidx<16>: k -> 24 k2 + pk, 256-k -> 24 (15-k2) + pq
       const int partner = gbase | ((16 - hl) & 15);
+      const int pk = kPStride * (hl >> 3) + (hl & 7);
+      const int pq = (hl == 0) ? 2 * kPStride : kPStride * ((16 - hl) >> 3) + ((16 - hl) & 7);
 #pragma unroll
       for (int k2 = 0; k2 < 8; ++k2) {
         const float sr = (hl == 0) ? xr[(16 - k2) & 15] : xr[15 - k2];
@@ -578,7 +608,7 @@ fused_features_512_kernel(const FastArgs a) {
         if (k == 0) {
           const float s0 = ar + ai, d0 = ar - ai;
           P[0] = s0 * s0;
-          P[256] = d0 * d0;
+          P[pidx<16>(256)] = d0 * d0;
         } else {
           const float2 w = s_tw2[k2 * 16 + hl];
           const float er = ar + cr, ei = ai - ci;      // 2E
@@ -586,15 +616,15 @@ fused_features_512_kernel(const FastArgs a) {
           const float orr = w.x * u - w.y * v, oi = w.x * v + w.y * u;   // 2 W O
           const float x1r = er + orr, x1i = ei + oi;
           const float x2r = er - orr, x2i = ei - oi;
-          P[k] = 0.25f * (x1r * x1r + x1i * x1i);
-          P[256 - k] = 0.25f * (x2r * x2r + x2i * x2i);
+          P[2 * kPStride * k2 + pk] = 0.25f * (x1r * x1r + x1i * x1i);
+          P[2 * kPStride * (15 - k2) + pq] = 0.25f * (x2r * x2r + x2i * x2i);
         }
       }
-      if (hl == 0) P[128] = xr[8] * xr[8] + xi[8] * xi[8];
+      if (hl == 0) P[pidx<16>(128)] = xr[8] * xr[8] + xi[8] * xi[8];
       __syncwarp();
 
       float *out_row = reinterpret_cast<float *>(a.out) + (row0 + fl) * a.ld_out;
-      feature_tail<16>(p, tt, P, s_grp + 272, log_energy, out_row, valid, hl);
+      feature_tail<16>(p, tt, P, s_grp + kPFloats, log_energy, out_row, valid, hl);
     }
   }
 }
@@ -870,14 +900,19 @@ static void fast_layout(const snb_plan *plan, FastSmemLayout *sm) {
   sm->dct = off; off += align_up((xo.kind == SNB_FEAT_MFCC ? xo.num_ceps * sm->dct_stride : 0) * 4, 16);
   sm->lifter = off; off += align_up(xo.num_ceps * 4, 16);
   sm->idft = off; off += align_up((xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0) * 4, 16);
-  sm->mel = off; off += align_up(p.mel_blob_stride * 4, 16);
+  sm->mel = off; off += align_up(p.mel_fast_words * 4, 16);
   sm->span_cap = align_up((plan->tile_frames - 1) * p.S + p.W + 16, 8);
   sm->pcm = off; off += align_up(sm->span_cap * 2, 16);
   // per-group buffers 16 banks apart (size = 16 mod 32 floats): the two
   // groups of a warp use the same offsets inside their buffers, and with a
-  // multiple of 32 every 32-bit access of the warp was a 2-way bank conflict
-  sm->grp_floats = align_up(std::max(16 * kXStride * 2, 272 + (p.B + 4) + (xo.lpc_order + 2) + 2 * (p.B + 2)), 32) + 16;
+  // multiple of 32 every 32-bit access of the warp was a 2-way bank conflict.
+  // Contents: the transpose buffer (16 x 17 float2), later the power spectrum
+  // [kPFloats] followed by the tail scratch (mel[B+4] | autocorrelation)
+  sm->grp_floats = align_up(std::max(16 * kXStride * 2, kPFloats + (p.B + 4) + (xo.lpc_order + 2)), 32) + 16;
   sm->grp = off; off += kFastGroups * sm->grp_floats * 4;
+  // run partials of the mel stage: one float4 per run, per warp
+  sm->part_floats = 4 * align_up(32 + p.B + 2, 2);
+  sm->part = off; off += (kFastThreads / 32) * sm->part_floats * 4;
   sm->bar = off; off += 16;
   sm->total = off;
 }
@@ -946,38 +981,52 @@ static int get_mel_blob(const snb_plan *plan, float warp, const std::vector<int3
     const int B = p.B;
     std::vector<float> loud;
     build_equal_loudness(mb.center_freqs, &loud);
+    int32_t *gen = blob.data() + p.mel_gen_off;
     for (int b = 0; b < B; ++b) {
-      blob[b] = mb.first[b];
-      blob[B + b] = mb.size[b];
-      blob[2 * B + b] = mb.offset[b];
-      std::memcpy(&blob[3 * B + b], &loud[b], 4);
+      std::memcpy(&blob[b], &loud[b], 4);
+      gen[b] = mb.first[b];
+      gen[B + b] = mb.size[b];
+      gen[2 * B + b] = mb.offset[b];
     }
-    std::memcpy(&blob[4 * B], mb.weights.data(), mb.weights.size() * 4);
-    // segment tables + longest-processing-time dealing of segments to lanes
-    int32_t *seg = blob.data() + p.mel_seg_off;
-    for (int sg = 0; sg <= B; ++sg) {
-      seg[sg] = mb.seg_first[sg];
-      seg[(B + 1) + sg] = mb.seg_size[sg];
-    }
-    int32_t *lane_seg = seg + 2 * (B + 1);
-    for (int i = 0; i < p.mel_nslots * 16; ++i) lane_seg[i] = -1;
-    std::vector<int> order(B + 1);
-    for (int i = 0; i <= B; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int a, int b2) { return mb.seg_size[a] > mb.seg_size[b2]; });
-    int load[16] = {0}, used[16] = {0};
-    for (int sg : order) {
-      int best = -1;
-      for (int l = 0; l < 16; ++l)
-        if (used[l] < p.mel_nslots && (best < 0 || load[l] < load[best])) best = l;
-      lane_seg[used[best] * 16 + best] = sg;
-      used[best] += 1;
-      load[best] += mb.seg_size[sg] + 2;
-    }
-    const int updown_off = p.mel_updown_off;
-    for (int i = 0; i < mb.num_fft_bins; ++i) {
-      std::memcpy(&blob[updown_off + 2 * i], &mb.up[i], 4);
-      std::memcpy(&blob[updown_off + 2 * i + 1], &mb.down[i], 4);
+    std::memcpy(gen + 3 * B, mb.weights.data(), mb.weights.size() * 4);
+    if (mb.num_fft_bins == 256) {
+      // fused path: bins dealt to the 32 lanes in chunks of 8; a run is a
+      // maximal stretch of bins of one segment inside one chunk.  Bins below
+      // the first / above the last triangle get the pseudo segments -1 / B+1
+      // (zero weights, their runs are never read back).
+      std::vector<int32_t> sg(256);
+      bool seen = false;
+      for (int k = 0; k < 256; ++k) {
+        sg[k] = mb.seg_of[k];
+        if (sg[k] >= 0) seen = true;
+        else if (seen) sg[k] = B + 1;
+      }
+      float *cw = reinterpret_cast<float *>(blob.data() + p.mel_chunk_off);
+      int32_t *meta = blob.data() + p.mel_meta_off;
+      int32_t *run_first = blob.data() + p.mel_run_off;
+      std::vector<int32_t> run_seg;
+      for (int l = 0; l < 32; ++l) {
+        uint32_t flags = 0;
+        const uint32_t first_run = static_cast<uint32_t>(run_seg.size());
+        for (int i = 0; i < 8; ++i) {
+          const int k = 8 * l + i;
+          cw[20 * l + 2 * i] = mb.up[k];
+          cw[20 * l + 2 * i + 1] = mb.down[k];
+          if (i == 7 || sg[k + 1] != sg[k]) {
+            flags |= 1u << i;
+            run_seg.push_back(sg[k]);
+          }
+        }
+        meta[l] = static_cast<int32_t>(flags | (first_run << 8));
+      }
+      for (size_t j = 1; j < run_seg.size(); ++j)
+        if (run_seg[j] < run_seg[j - 1])
+          return set_error(SNB_ERR_UNSUPPORTED, "non monotonic mel segments");
+      if (static_cast<int>(run_seg.size()) > 32 + B + 2)
+        return set_error(SNB_ERR_UNSUPPORTED, "too many mel runs (%zu)", run_seg.size());
+      for (int sgm = 0; sgm <= B + 1; ++sgm)
+        run_first[sgm] = static_cast<int32_t>(
+            std::lower_bound(run_seg.begin(), run_seg.end(), sgm) - run_seg.begin());
     }
     it = plan->mel_blobs.emplace(key, std::move(blob)).first;
   }
@@ -1058,12 +1107,12 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
   // validate the mel options now (KALDI_ERR at construction of the computer)
   if (needs_mel) {
     p.mel_wcap = 2 * (p.N / 2) + 2 * p.B + 8;
-    p.mel_seg_off = 4 * p.B + p.mel_wcap;
-    p.mel_nslots = (p.B + 1 + 15) / 16;
-    p.mel_updown_off = p.mel_seg_off + 2 * (p.B + 1) + p.mel_nslots * 16;
-    p.mel_updown_off += p.mel_updown_off & 1;
-    p.mel_blob_stride = p.mel_updown_off + 2 * (p.N / 2) + 2;
-    p.mel_blob_stride += p.mel_blob_stride & 1;
+    p.mel_chunk_off = align_up(p.B, 4);
+    p.mel_meta_off = p.mel_chunk_off + 32 * 20;
+    p.mel_run_off = p.mel_meta_off + 32;
+    p.mel_fast_words = align_up(p.mel_run_off + p.B + 2, 4);
+    p.mel_gen_off = p.mel_fast_words;
+    p.mel_blob_stride = align_up(p.mel_gen_off + 3 * p.B + p.mel_wcap, 4);
     const std::vector<int32_t> *blob;
     rc = get_mel_blob(plan, 1.0f, &blob);
     if (rc != SNB_OK) return fail(rc);
@@ -1438,7 +1487,11 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
     };
     int rc;
     static const bool no_w400 = getenv("SNB_FUSED_W400") && atoi(getenv("SNB_FUSED_W400")) == 0;
-    if (p.W == 400 && !no_w400)
+    static const bool occ2 = getenv("SNB_FUSED_OCC") && atoi(getenv("SNB_FUSED_OCC")) == 2;
+    static std::atomic<size_t> smem2{0};
+    if (p.W == 400 && occ2)
+      rc = launch(fused_features_512_kernel<2, 400>, &smem2);      // experiment: 128 registers
+    else if (p.W == 400 && !no_w400)
       rc = (plan->fused_occ == 4) ? launch(fused_features_512_kernel<4, 400>, &g_fast_smem4_w400)
                                   : launch(fused_features_512_kernel<3, 400>, &g_fast_smem_w400);
     else

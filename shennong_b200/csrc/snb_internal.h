@@ -61,6 +61,7 @@ struct MelBanksHost {
   // triangle s (weight up) and the falling side of triangle s-1 (weight down)
   std::vector<int32_t> seg_first, seg_size;   // [B+1]
   std::vector<float> up, down;                // [num_fft_bins]
+  std::vector<int32_t> seg_of;                // [num_fft_bins] segment of a bin, -1: outside every triangle
 };
 // returns SNB_OK or SNB_ERR_OPTION (sets error)
 int build_mel_banks(const snb_frame_opts &fo, const snb_mel_opts &mo,
@@ -73,8 +74,11 @@ void build_idft_bases(int32_t n_bases, int32_t dimension,
                       std::vector<float> *out);
 
 // ---- device-side views -------------------------------------------------------
-// mel "blob": one contiguous float/int block per VTLN warp value
-//   [ first[B] | size[B] | offset[B] | loudness[B] | weights[wcap] ]
+// mel "blob": one contiguous float/int block per VTLN warp value (words):
+//   [ loudness[B] | chunk_w[32*20] | chunk_meta[32] | run_first[B+2] |   <- fused kernel (staged in smem)
+//     first[B] | size[B] | offset[B] | weights[wcap] ]                   <- generic kernel (global memory)
+// chunk_*: FFT bins dealt to the 32 lanes of a warp in contiguous chunks of 8
+// (features.cu, "mel energies"); only built when the FFT has 256 bins.
 struct FeatTables {
   const float *window;     // [W]
   const float2 *tw_half;   // [N/2]  e^{-2 pi i m/(N/2)}  (fast path: W256^m)
@@ -93,9 +97,11 @@ struct FeatParams {
   int32_t dim;                // output columns
   int32_t mel_blob_stride;    // in 4-byte words
   int32_t mel_wcap;           // weights capacity per blob
-  int32_t mel_seg_off;        // word offset of the segment tables in a blob
-  int32_t mel_nslots;         // segments per lane (16-lane groups)
-  int32_t mel_updown_off;     // word offset (even) of the float2 (up, down) table
+  int32_t mel_chunk_off;      // word offset (multiple of 4) of chunk_w
+  int32_t mel_meta_off;       // word offset of chunk_meta
+  int32_t mel_run_off;        // word offset of run_first
+  int32_t mel_fast_words;     // words the fused kernel stages (multiple of 4)
+  int32_t mel_gen_off;        // word offset of first[] (generic-path sections)
   int32_t need_raw_energy, need_post_energy;
   float log_energy_floor;
   float eps_energy;           // FLT_EPSILON (Kaldi) or DBL_EPSILON (plp.py)

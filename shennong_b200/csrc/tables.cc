@@ -229,7 +229,8 @@ int build_mel_banks(const snb_frame_opts &fo, const snb_mel_opts &mo,
   out->seg_size.assign(B + 1, 0);
   out->up.assign(nfft, 0.0f);
   out->down.assign(nfft, 0.0f);
-  std::vector<int32_t> seg_of(nfft, -1);
+  std::vector<int32_t> &seg_of = out->seg_of;
+  seg_of.assign(nfft, -1);
   std::vector<float> bin_mel(nfft);
   for (int32_t i = 0; i < nfft; ++i) bin_mel[i] = hz_to_mel(bin_width * i);
   for (int32_t b = 0; b < B; ++b) {
