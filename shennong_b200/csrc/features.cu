@@ -69,6 +69,7 @@ struct TailTables {       // tables the tails read (shared memory in both paths)
   // buffers of the two lane groups (= frames) of a warp
   float4 *part;
   int grp_floats;
+  int mel_max_runs;       // longest run list of a segment (over the VTLN warps seen so far: plan-wide bound)
   MelView mel;
 };
 
@@ -224,9 +225,17 @@ __device__ __forceinline__ void feature_tail(const FeatParams &p, const TailTabl
       // runs added in bin order (deterministic)
       const float2 *mine = reinterpret_cast<const float2 *>(t.part) + ((threadIdx.x & 31) >> 4);
       const int r0 = t.mel.run_first[b], r1 = t.mel.run_first[b + 1], r2 = t.mel.run_first[b + 2];
+      // (blocks of four predicated steps up to the longest run list of the
+      // plan: uniform trip count, no divergent loop per lane)
       float u = 0.0f, d = 0.0f;
-      for (int j = r0; j < r1; ++j) u += mine[2 * j].x;
-      for (int j = r1; j < r2; ++j) d += mine[2 * j].y;
+      for (int j0 = 0; j0 < t.mel_max_runs; j0 += 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ju = r0 + j0 + i, jd = r1 + j0 + i;
+          if (ju < r1) u += mine[2 * ju].x;
+          if (jd < r2) d += mine[2 * jd].y;
+        }
+      }
       acc = u + d;
     } else {
       const int first = t.mel.first[b], size = t.mel.size[b];
@@ -331,6 +340,7 @@ struct FastArgs {
   int64_t ld_out;
   uint64_t seed;
   int use_tma;
+  int mel_max_runs;
 };
 
 // kMinBlocks = 3: 80 registers; kMinBlocks = 4: 64 registers (no spills), 32
@@ -398,6 +408,7 @@ fused_features_512_kernel(const FastArgs a) {
   tt.mel = mel_view(s_mel, p);
   tt.part = reinterpret_cast<float4 *>(smem + a.sm.part) + (tid >> 5) * (a.sm.part_floats / 4);
   tt.grp_floats = a.sm.grp_floats;
+  tt.mel_max_runs = a.mel_max_runs;
 
   const bool pair_ok_static = (S % 2) == 0;
   const float dither = p.fo.dither;
@@ -1027,6 +1038,10 @@ static int get_mel_blob(const snb_plan *plan, float warp, const std::vector<int3
       for (int sgm = 0; sgm <= B + 1; ++sgm)
         run_first[sgm] = static_cast<int32_t>(
             std::lower_bound(run_seg.begin(), run_seg.end(), sgm) - run_seg.begin());
+      // longest run list of a segment, kept in the spare word after run_first
+      int32_t longest = 1;
+      for (int sgm = 0; sgm <= B; ++sgm) longest = std::max(longest, run_first[sgm + 1] - run_first[sgm]);
+      run_first[B + 2] = longest;
     }
     it = plan->mel_blobs.emplace(key, std::move(blob)).first;
   }
@@ -1110,7 +1125,7 @@ extern "C" int snb_feature_plan_create(const snb_frame_opts *fo, const snb_mel_o
     p.mel_chunk_off = align_up(p.B, 4);
     p.mel_meta_off = p.mel_chunk_off + 32 * 20;
     p.mel_run_off = p.mel_meta_off + 32;
-    p.mel_fast_words = align_up(p.mel_run_off + p.B + 2, 4);
+    p.mel_fast_words = align_up(p.mel_run_off + p.B + 3, 4);     // run_first[B+2] + longest run list
     p.mel_gen_off = p.mel_fast_words;
     p.mel_blob_stride = align_up(p.mel_gen_off + 3 * p.B + p.mel_wcap, 4);
     const std::vector<int32_t> *blob;
@@ -1294,6 +1309,7 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
           if (rc != SNB_OK) return fail(rc);
           it = index.emplace(key, static_cast<int32_t>(index.size())).first;
           blobs.insert(blobs.end(), blob->begin(), blob->end());
+          b->mel_max_runs = std::max(b->mel_max_runs, (*blob)[plan->params.mel_run_off + plan->params.B + 2]);
         }
         utt_mel[u] = it->second;
       }
@@ -1304,6 +1320,7 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
         if (rc != SNB_OK) return fail(rc);
         blobs = *blob;
         b->nblobs = 1;
+        b->mel_max_runs = (*blob)[plan->params.mel_run_off + plan->params.B + 2];
       }
       o_mel = add_section(blobs.data(), blobs.size() * sizeof(int32_t));
       has_mel = true;
@@ -1475,6 +1492,9 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
     a.seed = seed;
     static const bool no_tma = getenv("SNB_NO_TMA") != nullptr;
     a.use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(d_pcm) % 16 == 0)) ? 1 : 0;
+    // a segment of n bins meets at most (n + 6) / 8 + 1 chunks of 8 bins; the
+    // widest possible segment is the whole spectrum
+    a.mel_max_runs = batch->mel_max_runs > 0 ? batch->mel_max_runs : 33;
     auto launch = [&](auto kernel, std::atomic<size_t> *state) -> int {
       int rc = ensure_smem(kernel, a.sm.total, state);
       if (rc != SNB_OK) return rc;

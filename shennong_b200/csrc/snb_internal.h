@@ -75,7 +75,7 @@ void build_idft_bases(int32_t n_bases, int32_t dimension,
 
 // ---- device-side views -------------------------------------------------------
 // mel "blob": one contiguous float/int block per VTLN warp value (words):
-//   [ loudness[B] | chunk_w[32*20] | chunk_meta[32] | run_first[B+2] |   <- fused kernel (staged in smem)
+//   [ loudness[B] | chunk_w[32*20] | chunk_meta[32] | run_first[B+2] | longest run list |   <- fused kernel (smem)
 //     first[B] | size[B] | offset[B] | weights[wcap] ]                   <- generic kernel (global memory)
 // chunk_*: FFT bins dealt to the 32 lanes of a warp in contiguous chunks of 8
 // (features.cu, "mel energies"); only built when the FFT has 256 bins.
@@ -194,6 +194,7 @@ struct snb_batch {
   int64_t ntiles = 0;
   int32_t *d_mel_blobs = nullptr;  // [nblobs, mel_blob_stride]
   int32_t nblobs = 0;
+  int32_t mel_max_runs = 0;        // longest per-segment run list over the blobs (fused mel stage)
   // pitch
   std::vector<int64_t> down_offsets;   // per-utt offsets in downsampled signal
   int64_t *d_down_offsets = nullptr;

@@ -44,6 +44,22 @@ def test_all_golden_vectors(golden):
             raise AssertionError(f'{name}: {err}') from None
 
 
+def test_plp_vs_reference_plp_py(golden_plp):
+    """PLP / RASTA-PLP (fused kernel, RASTA workspace path, VTLN, generic FFT
+    path) against the outputs of the reference's own plp.py, times included"""
+    data, meta = golden_plp
+    pcm = data['pcm']
+    for name, entry in meta.items():
+        warp = entry['vtln_warp']
+        feats = run('plp', pcm, vtln_warp=None if warp == 1.0 else warp,
+                    **entry['kwargs'])
+        try:
+            scale_close(feats.data, data[name], tol=1e-4)
+        except AssertionError as err:
+            raise AssertionError(f'{name}: {err}') from None
+        assert np.array_equal(feats.times, data[name + '.times']), name
+
+
 @pytest.mark.parametrize('kind,kwargs', [
     ('mfcc', {}),
     ('mfcc', {'use_energy': False, 'htk_compat': True}),
