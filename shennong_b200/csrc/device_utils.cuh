@@ -67,6 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!done);
 }
 
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that occupy no registers
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- counter-based noise for dither ----------------------------------------
 // splitmix64 finaliser: two independent 32-bit uniforms per (seed, frame, pair)
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {

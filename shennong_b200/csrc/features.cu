@@ -312,7 +312,7 @@ constexpr int kFastGroups = 16;         // half-warps per CTA
 constexpr int kXStride = 17;            // float2 row stride of the transpose buffer
 
 struct FastSmemLayout {                 // byte offsets into dynamic smem
-  int window, tw1, tw2, dct, lifter, idft, mel, pcm, grp, part, bar, total;
+  int window, tw1, tw2, dct, lifter, idft, mel, pcm, grp, part, desc, bar, total;
   int grp_floats, span_cap, dct_stride, part_floats;
 };
 
@@ -343,6 +343,23 @@ struct FastArgs {
   int mel_max_runs;
 };
 
+// the 16-byte aligned piece of the packed PCM buffer that covers a tile;
+// false when the tile has to be gathered element by element
+struct TileSpan {
+  int64_t gstart;      // first sample of the bulk copy (multiple of 8)
+  uint32_t bytes;      // multiple of 16
+  int mis;             // samples between gstart and the tile's first sample
+};
+__device__ __forceinline__ bool tile_span(const TileDesc &td, const FastArgs &a, int S, int W, TileSpan *out) {
+  if (!a.use_tma || td.g0 < 0) return false;
+  const int span = (td.nf - 1) * S + W;
+  out->mis = static_cast<int>(td.g0 & 7);
+  out->gstart = td.g0 - out->mis;
+  const int64_t nsamp = (static_cast<int64_t>(span) + out->mis + 7) & ~7ll;
+  out->bytes = static_cast<uint32_t>(nsamp * 2);
+  return out->gstart + nsamp <= a.total_samples;
+}
+
 // kMinBlocks = 3: 80 registers; kMinBlocks = 4: 64 registers (no spills), 32
 // resident warps per SM -- selected at plan time when the shared memory of four
 // CTAs fits (SNB_FUSED_OCC=3|4 overrides).
@@ -364,7 +381,8 @@ fused_features_512_kernel(const FastArgs a) {
   int32_t *s_mel = reinterpret_cast<int32_t *>(smem + a.sm.mel);
   int16_t *s_pcm = reinterpret_cast<int16_t *>(smem + a.sm.pcm);
   float *s_grp_all = reinterpret_cast<float *>(smem + a.sm.grp);
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.sm.bar);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.sm.bar);          // [2]
+  TileDesc *s_desc = reinterpret_cast<TileDesc *>(smem + a.sm.desc);        // ring of 3
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -397,11 +415,12 @@ fused_features_512_kernel(const FastArgs a) {
   if (kind == SNB_FEAT_PLP)
     for (int i = tid; i < (xo.lpc_order + 1) * (B + 2); i += kFastThreads) s_idft[i] = p.t.idft[i];
   if (tid == 0) {
-    mbar_init(s_bar, 1);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
     fence_barrier_init();
   }
   int cur_mel = -1;
-  uint32_t parity = 0;
+  uint32_t parity = 0;               // bit b: phase of the mbarrier of PCM buffer b
   TailTables tt;
   tt.dct = s_dct; tt.lifter = s_lifter; tt.idft = s_idft;
   tt.dct_stride = a.sm.dct_stride;
@@ -414,58 +433,83 @@ fused_features_512_kernel(const FastArgs a) {
   const float dither = p.fo.dither;
   const int nfull = W / 32;           // n1 iterations with 32 valid samples
 
-  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const TileDesc td = a.tiles[tile];
-    __syncthreads();   // previous tile fully consumed (s_pcm, s_mel) + tables visible
+  // Software pipeline over the CTA's tiles (tile = up to 16 frames of one
+  // utterance, one frame per lane group): while tile i is computed, the PCM
+  // span of tile i+1 is already in flight (TMA bulk copy into the other
+  // buffer, completion on that buffer's mbarrier) and the descriptor of tile
+  // i+2 is being fetched by cp.async into a ring of three.  One CTA barrier
+  // per tile.
+  const int64_t stride = gridDim.x;
+  if (tid == 0 && blockIdx.x < a.ntiles) {
+    s_desc[0] = a.tiles[blockIdx.x];
+    if (blockIdx.x + stride < a.ntiles) s_desc[1] = a.tiles[blockIdx.x + stride];
+    TileSpan sp;
+    if (tile_span(s_desc[0], a, S, W, &sp)) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&s_bar[0], sp.bytes);
+      bulk_copy_g2s(s_pcm, a.pcm + sp.gstart, sp.bytes, &s_bar[0]);
+    }
+  }
+  __syncthreads();                   // tables, barriers and the first descriptors are visible
+  int slot = 0, buf = 0;
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += stride) {
+    const TileDesc td = s_desc[slot];
+    const int slot1 = (slot == 2) ? 0 : slot + 1, slot2 = (slot1 == 2) ? 0 : slot1 + 1;
+    if (tid == 0) {
+      // buffer buf^1 and ring slot slot2 were last read before the barrier
+      // that ended the previous iteration
+      if (tile + stride < a.ntiles) {
+        TileSpan sp;
+        if (tile_span(s_desc[slot1], a, S, W, &sp)) {
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&s_bar[buf ^ 1], sp.bytes);
+          bulk_copy_g2s(s_pcm + (buf ^ 1) * a.sm.span_cap, a.pcm + sp.gstart, sp.bytes, &s_bar[buf ^ 1]);
+        }
+      }
+      if (tile + 2 * stride < a.ntiles) {
+        const TileDesc *src = a.tiles + (tile + 2 * stride);
+        cp_async_16(&s_desc[slot2], src);
+        cp_async_16(reinterpret_cast<char *>(&s_desc[slot2]) + 16, reinterpret_cast<const char *>(src) + 16);
+        cp_async_commit();
+      }
+    }
     if (B > 0 && td.mel_idx != cur_mel) {
+      // (the barrier that ended the previous iteration freed s_mel)
       const int32_t *src = a.mel_blobs + static_cast<int64_t>(td.mel_idx) * p.mel_blob_stride;
       for (int i = tid; i < p.mel_fast_words; i += kFastThreads) s_mel[i] = src[i];
       cur_mel = td.mel_idx;
+      __syncthreads();
     }
-    // ---- stage the PCM span of this tile ----
-    const int64_t utt_off = a.sample_begin[td.utt];
-    const int64_t utt_len = a.sample_len[td.utt];
-    const int64_t a0 = first_sample_of_frame_dev(td.f0, p);      // may be < 0
-    const int span = (td.nf - 1) * S + W;
-    int mis = 0;                                                 // samples of misalignment
-    const bool inside = (a0 >= 0) && (a0 + span <= utt_len);
-    bool tma = false;
-    if (a.use_tma && inside) {
-      const int64_t g0 = utt_off + a0;
-      mis = static_cast<int>(g0 & 7);
-      const int64_t gstart = g0 - mis;
-      const int64_t nsamp = (static_cast<int64_t>(span) + mis + 7) & ~7ll;
-      tma = (gstart + nsamp <= a.total_samples);
-      if (tma) {
-        if (tid == 0) {
-          fence_proxy_async();
-          const uint32_t bytes = static_cast<uint32_t>(nsamp * 2);
-          mbar_arrive_expect_tx(s_bar, bytes);
-          bulk_copy_g2s(s_pcm, a.pcm + gstart, bytes, s_bar);
-        }
-      } else {
-        mis = 0;
-      }
-    }
-    if (!tma) {
+    // ---- the PCM span of this tile ----
+    int16_t *pcm_buf = s_pcm + buf * a.sm.span_cap;
+    TileSpan sp;
+    const bool tma = tile_span(td, a, S, W, &sp);
+    const int mis = tma ? sp.mis : 0;              // samples of misalignment
+    if (tma) {
+      mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
+      parity ^= 1u << buf;
+    } else {
       // element loads with reflection at the utterance edges (snip_edges=False,
-      // ExtractWindow restated at plp.py:239-254) or unaligned tail tiles
-      const int16_t *src = a.pcm + utt_off;
+      // ExtractWindow restated at plp.py:239-254) or spans that cannot be
+      // bulk-copied (unaligned buffer, end of the allocation)
+      const int64_t utt_len = a.sample_len[td.utt];
+      const int16_t *src = a.pcm + a.sample_begin[td.utt];
+      const int64_t a0 = first_sample_of_frame_dev(td.f0, p);      // may be < 0
+      const int span = (td.nf - 1) * S + W;
       for (int i = tid; i < span; i += kFastThreads) {
         int64_t k = a0 + i;
         while (k < 0 || k >= utt_len) k = (k < 0) ? (-k - 1) : (2 * utt_len - 1 - k);
-        s_pcm[i] = src[k];
+        pcm_buf[i] = src[k];
       }
+      __syncthreads();
     }
-    if (tma) { mbar_wait(s_bar, parity); parity ^= 1u; }
-    __syncthreads();
 
-    const int64_t row0 = a.frame_offsets[td.utt] + td.f0;
-    for (int base = 0; base < td.nf; base += kFastGroups) {
-      const int fl = base + grp;
+    const int64_t row0 = td.row0;
+    do {                             // one frame per lane group (`break` = frame done)
+      const int fl = grp;
       const bool valid = fl < td.nf;
       const int fidx = valid ? fl : td.nf - 1;     // idle groups redo the last frame
-      const int16_t *fr = s_pcm + mis + fidx * S;
+      const int16_t *fr = pcm_buf + mis + fidx * S;
       const bool pair_ok = pair_ok_static && ((mis & 1) == 0);
       float xr[16], xi[16];
       // ---- load + int16 -> float (+ dither) ----
@@ -567,7 +611,7 @@ fused_features_512_kernel(const FastArgs a) {
         if (valid && hl == 0)
           reinterpret_cast<double *>(a.out)[(row0 + fl) * a.ld_out] =
               compress_energy(e, xo.energy_compression);
-        continue;
+        break;
       }
       if (p.need_post_energy) {
         float e = 0.0f;
@@ -636,7 +680,11 @@ fused_features_512_kernel(const FastArgs a) {
 
       float *out_row = reinterpret_cast<float *>(a.out) + (row0 + fl) * a.ld_out;
       feature_tail<16>(p, tt, P, s_grp + kPFloats, log_energy, out_row, valid, hl);
-    }
+    } while (false);
+    if (tid == 0) cp_async_wait_all();   // descriptor of tile i+2 landed (visible after the barrier)
+    __syncthreads();                     // this tile's PCM buffer, s_mel and ring slot are free
+    slot = slot1;
+    buf ^= 1;
   }
 }
 
@@ -850,7 +898,6 @@ struct PlpMelArgs {
   int64_t ld_mel;
   const int64_t *frame_offsets;
   const int32_t *utt_mel_idx;   // may be NULL (blob 0)
-  const TileDesc *tiles;        // fast-path batches carry the mel index per tile
   const int32_t *mel_blobs;
   int64_t nutts, total_frames;
   float *out;
@@ -893,6 +940,34 @@ __global__ void __launch_bounds__(kGenWarps * 32) plp_from_mel_kernel(const PlpM
 }
 
 // ---------------------------------------------------------------------------
+// tile table of a fused-path batch, expanded on the device from O(utterances)
+// host data: utterance u owns tiles [tile_first[u], tile_first[u+1]) of T frames
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) expand_tiles_kernel(
+    TileDesc *out, const int64_t *tile_first, const int64_t *sample_begin, const int64_t *sample_len,
+    const int64_t *frame_offsets, const int32_t *utt_mel, int64_t nutts, int T, int S, int W, int snip_edges) {
+  for (int64_t u = blockIdx.x; u < nutts; u += gridDim.x) {
+    const int64_t t0 = tile_first[u], nt = tile_first[u + 1] - t0;
+    const int64_t row0 = frame_offsets[u], nf_utt = frame_offsets[u + 1] - row0;
+    const int64_t begin = sample_begin[u], len = sample_len[u];
+    const int32_t mel_idx = utt_mel ? utt_mel[u] : 0;
+    for (int64_t t = threadIdx.x; t < nt; t += blockDim.x) {
+      TileDesc td;
+      td.utt = static_cast<int32_t>(u);
+      td.f0 = static_cast<int32_t>(t * T);
+      td.nf = static_cast<int32_t>(nf_utt - t * T < T ? nf_utt - t * T : T);
+      td.mel_idx = mel_idx;
+      td.row0 = row0 + td.f0;
+      const int64_t a0 = snip_edges ? static_cast<int64_t>(td.f0) * S
+                                    : static_cast<int64_t>(td.f0) * S + S / 2 - W / 2;
+      const int64_t span = static_cast<int64_t>(td.nf - 1) * S + W;
+      td.g0 = (a0 >= 0 && a0 + span <= len) ? begin + a0 : -1;
+      out[t0 + t] = td;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host: plan
 // ---------------------------------------------------------------------------
 static int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -913,7 +988,7 @@ static void fast_layout(const snb_plan *plan, FastSmemLayout *sm) {
   sm->idft = off; off += align_up((xo.kind == SNB_FEAT_PLP ? (xo.lpc_order + 1) * (p.B + 2) : 0) * 4, 16);
   sm->mel = off; off += align_up(p.mel_fast_words * 4, 16);
   sm->span_cap = align_up((plan->tile_frames - 1) * p.S + p.W + 16, 8);
-  sm->pcm = off; off += align_up(sm->span_cap * 2, 16);
+  sm->pcm = off; off += 2 * sm->span_cap * 2;                   // double buffered
   // per-group buffers 16 banks apart (size = 16 mod 32 floats): the two
   // groups of a warp use the same offsets inside their buffers, and with a
   // multiple of 32 every 32-bit access of the warp was a 2-way bank conflict.
@@ -924,6 +999,7 @@ static void fast_layout(const snb_plan *plan, FastSmemLayout *sm) {
   // run partials of the mel stage: one float4 per run, per warp
   sm->part_floats = 4 * align_up(32 + p.B + 2, 2);
   sm->part = off; off += (kFastThreads / 32) * sm->part_floats * 4;
+  sm->desc = off; off += 3 * static_cast<int>(sizeof(TileDesc));
   sm->bar = off; off += 16;
   sm->total = off;
 }
@@ -934,27 +1010,16 @@ int feature_plan_finalize(snb_plan *plan) {
   plan->fast_path = false;
   const int group_need = (xo.kind == SNB_FEAT_PLP) ? xo.lpc_order + 1 : 1;
   if (p.N == 512 && p.W > 256 && p.B <= 200 && group_need <= 16) {
-    // tile so that the staged span stays small (<= 24 KB of int16); prefer
-    // the tile size that lets four CTAs share an SM
+    // one frame per lane group and tile; fewer when a huge frame shift would
+    // make the double-buffered span larger than 2 x 24 KB
     static const int forced_occ = getenv("SNB_FUSED_OCC") ? atoi(getenv("SNB_FUSED_OCC")) : 0;
-    int t = 32;
+    int t = kFastGroups;
     while (t > 1 && ((t - 1) * p.S + p.W + 16) * 2 > 24 * 1024) t /= 2;
     plan->tile_frames = t;
-    plan->fused_occ = 3;
     FastSmemLayout sm;
     fast_layout(plan, &sm);
     const int budget4 = (227 * 1024) / 4 - 2048;     // per CTA, minus static + reserved
-    if (forced_occ != 3) {
-      if (sm.total <= budget4) {
-        plan->fused_occ = 4;
-      } else if (t >= 32) {
-        plan->tile_frames = 16;
-        FastSmemLayout sm16;
-        fast_layout(plan, &sm16);
-        if (sm16.total <= budget4) { plan->fused_occ = 4; sm = sm16; }
-        else plan->tile_frames = t;
-      }
-    }
+    plan->fused_occ = (sm.total <= budget4 && forced_occ != 3) ? 4 : 3;
     if (sm.total <= 200 * 1024) {
       plan->fast_path = true;
       plan->smem_bytes = sm.total;
@@ -1285,8 +1350,8 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
   const size_t o_begin = add_section(b->sample_begin.data(), nutts * sizeof(int64_t));
   const size_t o_len = add_section(b->sample_len.data(), nutts * sizeof(int64_t));
   const size_t o_foff = add_section(b->frame_offsets.data(), (nutts + 1) * sizeof(int64_t));
-  size_t o_down = 0, o_mel = 0, o_tiles = 0;
-  bool has_down = false, has_mel = false, has_tiles = false;
+  size_t o_down = 0, o_mel = 0, o_uttmel = 0, o_tfirst = 0;
+  bool has_down = false, has_mel = false, has_tiles = false, has_uttmel = false;
   if (plan->kind == 1) {
     int rc = pitch_batch_init(plan, b);
     if (rc != SNB_OK) return fail(rc);
@@ -1325,30 +1390,25 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
       o_mel = add_section(blobs.data(), blobs.size() * sizeof(int32_t));
       has_mel = true;
     }
-    // ---- tile table (fast path) or per-utterance mel index (generic) ----
+    // ---- per-utterance mel index; fused path: first tile of every utterance
+    //      (the tile table itself is expanded on the device, see below) ----
+    o_uttmel = add_section(utt_mel.data(), nutts * sizeof(int32_t));
+    has_uttmel = true;
     if (plan->fast_path) {
-      std::vector<TileDesc> tiles;
       const int T = plan->tile_frames;
-      tiles.reserve(static_cast<size_t>(b->total_frames / T + nutts));
+      std::vector<int64_t> tile_first(nutts + 1, 0);
       for (int64_t u = 0; u < nutts; ++u) {
         const int64_t nf = b->frame_offsets[u + 1] - b->frame_offsets[u];
-        for (int64_t f0 = 0; f0 < nf; f0 += T) {
-          TileDesc td;
-          td.utt = static_cast<int32_t>(u);
-          td.f0 = static_cast<int32_t>(f0);
-          td.nf = static_cast<int32_t>(std::min<int64_t>(T, nf - f0));
-          td.mel_idx = utt_mel[u];
-          tiles.push_back(td);
-        }
+        tile_first[u + 1] = tile_first[u] + (nf + T - 1) / T;
       }
-      b->ntiles = static_cast<int64_t>(tiles.size());
-      o_tiles = add_section(tiles.data(), tiles.size() * sizeof(TileDesc));
-      has_tiles = true;
-    } else {
-      o_tiles = add_section(utt_mel.data(), nutts * sizeof(int32_t));
+      b->ntiles = tile_first[nutts];
+      o_tfirst = add_section(tile_first.data(), tile_first.size() * sizeof(int64_t));
       has_tiles = true;
     }
   }
+  // device-only tail of the blob: the expanded tile table
+  const size_t o_tiles = (stage.size() + 15) / 16 * 16;
+  const size_t blob_bytes = o_tiles + (has_tiles ? static_cast<size_t>(b->ntiles) * sizeof(TileDesc) : 0) + 16;
   unsigned char *d = nullptr;
   cudaError_t e;
   if (on_stream) {
@@ -1357,7 +1417,7 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
     int dev = 0;
     cudaGetDevice(&dev);
     PoolBlock host;
-    e = device_pool().acquire(stage.size() + 16, dev, &b->dev_block);
+    e = device_pool().acquire(blob_bytes, dev, &b->dev_block);
     if (e == cudaSuccess) e = pinned_pool().acquire(stage.size() + 16, dev, &host);
     if (e == cudaSuccess) {
       b->pooled = true;
@@ -1378,7 +1438,7 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
       return fail(set_error(SNB_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(e)));
     }
   } else {
-    e = cudaMalloc(&d, stage.size() + 16);
+    e = cudaMalloc(&d, blob_bytes);
     if (e == cudaSuccess) e = upload(d, stage.data(), stage.size());
     if (e != cudaSuccess) {
       if (d) cudaFree(d);
@@ -1391,7 +1451,25 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
   b->d_frame_offsets = reinterpret_cast<int64_t *>(d + o_foff);
   if (has_down) b->d_down_offsets = reinterpret_cast<int64_t *>(d + o_down);
   if (has_mel) b->d_mel_blobs = reinterpret_cast<int32_t *>(d + o_mel);
-  if (has_tiles) b->d_tiles = reinterpret_cast<TileDesc *>(d + o_tiles);
+  if (has_uttmel) b->d_utt_mel = reinterpret_cast<int32_t *>(d + o_uttmel);
+  if (has_tiles && b->ntiles > 0) {
+    b->d_tile_first = reinterpret_cast<int64_t *>(d + o_tfirst);
+    b->d_tiles = reinterpret_cast<TileDesc *>(d + o_tiles);
+    // expand the tile table on the device, ordered after the upload
+    cudaStream_t s = stream;
+    if (!on_stream) e = upload_stream(&s);
+    if (e == cudaSuccess) {
+      const FeatParams &p = plan->params;
+      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(nutts, 8192));
+      expand_tiles_kernel<<<grid, 64, 0, s>>>(b->d_tiles, b->d_tile_first, b->d_sample_begin, b->d_sample_len,
+                                              b->d_frame_offsets, b->d_utt_mel, nutts, plan->tile_frames, p.S, p.W,
+                                              p.fo.snip_edges);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      e = cudaGetLastError();
+      if (e == cudaSuccess && !on_stream) e = cudaStreamSynchronize(s);
+    }
+    if (e != cudaSuccess) return fail(set_error(SNB_ERR_CUDA, "tile table expansion failed: %s", cudaGetErrorString(e)));
+  }
   *out = b;
   return SNB_OK;
 }
@@ -1538,7 +1616,7 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
   g.sample_begin = batch->d_sample_begin;
   g.sample_len = batch->d_sample_len;
   g.frame_offsets = batch->d_frame_offsets;
-  g.utt_mel_idx = plan->fast_path ? nullptr : reinterpret_cast<const int32_t *>(batch->d_tiles);
+  g.utt_mel_idx = batch->d_utt_mel;
   g.mel_blobs = batch->d_mel_blobs;
   g.pcm = d_pcm;
   g.pcm_f32 = d_wave;
@@ -1595,8 +1673,7 @@ extern "C" int snb_compute_features_ws(const snb_plan *plan, const snb_batch *ba
   a.mel = mel;
   a.ld_mel = ld_mel;
   a.frame_offsets = batch->d_frame_offsets;
-  a.utt_mel_idx = plan->fast_path ? nullptr : reinterpret_cast<const int32_t *>(batch->d_tiles);
-  a.tiles = plan->fast_path ? batch->d_tiles : nullptr;
+  a.utt_mel_idx = batch->d_utt_mel;
   a.mel_blobs = batch->d_mel_blobs;
   a.nutts = batch->nutts;
   a.total_frames = batch->total_frames;

@@ -41,6 +41,8 @@ extern std::atomic<int64_t> g_launch_count;
 // DMA only ordered in the legacy stream -- kernels launched on non-blocking
 // streams (PyTorch's) could then read the destination too early.
 cudaError_t upload(void *dst, const void *src, size_t bytes);
+// the calling thread's private non-blocking stream used by upload()
+cudaError_t upload_stream(cudaStream_t *out);
 
 // ---- host-side tables (tables.cc) ------------------------------------------
 int32_t window_size(const snb_frame_opts &o);
@@ -110,11 +112,14 @@ struct FeatParams {
 
 struct PitchTables;          // pitch.cu
 
-struct TileDesc {            // one CTA work item: frames [f0, f0+nf) of utt
+struct alignas(16) TileDesc {   // one CTA work item: frames [f0, f0+nf) of utt (32 bytes)
   int32_t utt;
   int32_t f0;
   int32_t nf;
   int32_t mel_idx;
+  int64_t row0;                // first output row of the tile
+  int64_t g0;                  // index in the packed PCM buffer of the tile's first sample when its
+                               // whole span lies inside the utterance (bulk-copyable), else -1
 };
 
 }  // namespace snb
@@ -190,8 +195,10 @@ struct snb_batch {
   std::vector<int64_t> sample_begin, sample_len, frame_offsets;
   void *d_blob = nullptr;            // single device allocation; the pointers below alias it
   int64_t *d_sample_begin = nullptr, *d_sample_len = nullptr, *d_frame_offsets = nullptr;
-  snb::TileDesc *d_tiles = nullptr;
+  snb::TileDesc *d_tiles = nullptr;      // fused path: expanded on the device from d_tile_first
   int64_t ntiles = 0;
+  int64_t *d_tile_first = nullptr;       // [nutts + 1] first tile of every utterance
+  int32_t *d_utt_mel = nullptr;          // [nutts] mel blob of every utterance
   int32_t *d_mel_blobs = nullptr;  // [nblobs, mel_blob_stride]
   int32_t nblobs = 0;
   int32_t mel_max_runs = 0;        // longest per-segment run list over the blobs (fused mel stage)

@@ -26,8 +26,7 @@ int set_error(int code, const char *fmt, ...) {
 }
 const char *last_error() { return g_error; }
 
-cudaError_t upload(void *dst, const void *src, size_t bytes) {
-  if (bytes == 0) return cudaSuccess;
+cudaError_t upload_stream(cudaStream_t *out) {
   static thread_local cudaStream_t stream = nullptr;
   static thread_local int stream_device = -1;
   int dev = 0;
@@ -38,6 +37,15 @@ cudaError_t upload(void *dst, const void *src, size_t bytes) {
     if (e != cudaSuccess) return e;
     stream_device = dev;
   }
+  *out = stream;
+  return cudaSuccess;
+}
+
+cudaError_t upload(void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  cudaStream_t stream = nullptr;
+  cudaError_t e = upload_stream(&stream);
+  if (e != cudaSuccess) return e;
   e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return e;
   return cudaStreamSynchronize(stream);
