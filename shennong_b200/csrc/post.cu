@@ -180,6 +180,115 @@ __global__ void __launch_bounds__(256) delta_tiled_kernel(const DeltaArgs a, con
   }
 }
 
+// Compile-time (ORDER, WINDOW) variant for the reference's defaults (delta
+// window 2, order 1 or 2): 128-row tiles, tap weights read as constant-bank
+// operands, the utterance of a tile found by a CTA-wide two-round search
+// instead of one thread's dependent binary search, and -- for the ~94 % of the
+// tiles that lie inside one utterance together with their halo -- no per-row
+// bounds, no clamping and one normalisation row.
+constexpr int kFixedTile = 128;
+
+// first u with offsets[u] <= row < offsets[u + 1]; every thread of the CTA
+// must call it (256 probes per round, __syncthreads_count as the vote)
+__device__ __forceinline__ int64_t cta_find_utt_row(const int64_t *offsets, int64_t nutts, int64_t row) {
+  int64_t lo = 0, hi = nutts;
+  while (hi - lo > 1) {
+    const int64_t step = (hi - lo + 255) / 256;
+    const int64_t probe = lo + (static_cast<int64_t>(threadIdx.x) + 1) * step;
+    const int ok = (probe < hi) && (offsets[probe] <= row);
+    const int k = __syncthreads_count(ok);
+    lo += k * step;
+    hi = min(lo + step, hi);
+  }
+  return lo;
+}
+
+template <int ORDER, int WINDOW>
+__global__ void __launch_bounds__(256) delta_fixed_kernel(const DeltaArgs a) {
+  constexpr int HALO = ORDER * WINDOW;
+  constexpr int NLOAD = kFixedTile + 2 * HALO;
+  extern __shared__ float s_x[];                        // [NLOAD, dim]
+  __shared__ int s_lo[NLOAD], s_hi[NLOAD];              // clamp bounds (tile rows), mixed tiles only
+  __shared__ int32_t s_group[NLOAD];
+  const int tid = threadIdx.x;
+  const int dim = a.dim;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kFixedTile;
+  const int64_t lo = row0 - HALO;
+  const int nrows = static_cast<int>(min(static_cast<int64_t>(kFixedTile), a.total_frames - row0));
+  const int64_t u0 = cta_find_utt_row(a.frame_offsets, a.nutts, lo < 0 ? 0 : lo);
+  const int64_t first0 = a.frame_offsets[u0], next0 = a.frame_offsets[u0 + 1];
+  const bool uniform = first0 <= lo && lo + NLOAD <= next0;     // tile + halo inside utterance u0
+  const bool do_norm = a.norm != nullptr;
+  if (!uniform) {
+    for (int i = tid; i < NLOAD; i += 256) {
+      const int64_t row = lo + i;
+      int rlo = 0, rhi = -1, g = 0;
+      if (row >= 0 && row < a.total_frames) {
+        int64_t u = u0, first = first0, next = next0;
+        if (row >= next) {
+          u = find_utt_row(a.frame_offsets, a.nutts, row);
+          first = a.frame_offsets[u]; next = a.frame_offsets[u + 1];
+        }
+        rlo = static_cast<int>(max(first - lo, static_cast<int64_t>(0)));
+        rhi = static_cast<int>(min(next - 1 - lo, static_cast<int64_t>(NLOAD - 1)));
+        g = a.utt_group ? a.utt_group[u] : static_cast<int32_t>(u);
+      }
+      s_lo[i] = rlo; s_hi[i] = rhi; s_group[i] = g;
+    }
+    __syncthreads();
+  }
+  // ---- stage the normalised rows (flat, coalesced) ----
+  {
+    const int32_t g0 = (uniform && do_norm) ? (a.utt_group ? a.utt_group[u0] : static_cast<int32_t>(u0)) : 0;
+    int i = tid / dim, d = tid - i * dim;
+    const int step_i = 256 / dim, step_d = 256 - step_i * dim;
+    for (int e = tid; e < NLOAD * dim; e += 256) {
+      float x = 0.0f;
+      if (uniform || s_hi[i] >= s_lo[i]) {
+        x = a.in[(lo + i) * a.ld_in + d];
+        if (do_norm) {
+          // ApplyCmvn: MulColsVec then AddVecToRows (two roundings)
+          const float *n = a.norm + static_cast<int64_t>(uniform ? g0 : s_group[i]) * 2 * dim;
+          x = __fadd_rn(__fmul_rn(x, n[dim + d]), n[d]);
+        }
+      }
+      s_x[e] = x;
+      i += step_i; d += step_d;
+      if (d >= dim) { d -= dim; ++i; }
+    }
+  }
+  __syncthreads();
+  // ---- one thread per (row, d): all orders from one pass over the halo ----
+  {
+    int r = tid / dim, d = tid - r * dim;
+    const int step_r = 256 / dim, step_d = 256 - step_r * dim;
+    for (int e = tid; e < nrows * dim; e += 256) {
+      float x[2 * HALO + 1];
+      if (uniform) {
+#pragma unroll
+        for (int j = 0; j <= 2 * HALO; ++j) x[j] = s_x[(r + j) * dim + d];
+      } else {
+        const int i0 = r + HALO, clo = s_lo[i0], chi = s_hi[i0];
+#pragma unroll
+        for (int j = 0; j <= 2 * HALO; ++j) x[j] = s_x[min(max(r + j, clo), chi) * dim + d];
+      }
+      float *o_row = a.out + (row0 + r) * a.ld_out + d;
+      int off = 0;                                  // taps of order o start at sum_{i<o} (2 i WINDOW + 1)
+#pragma unroll
+      for (int o = 0; o <= ORDER; ++o) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = -o * WINDOW; j <= o * WINDOW; ++j)
+          acc = fmaf(a.taps[off + o * WINDOW + j], x[HALO + j], acc);
+        o_row[o * dim] = acc;
+        off += 2 * o * WINDOW + 1;
+      }
+      r += step_r; d += step_d;
+      if (d >= dim) { d -= dim; ++r; }
+    }
+  }
+}
+
 static int build_delta_taps(int order, int window, DeltaArgs *a) {
   if (order < 0 || order > 7) return set_error(SNB_ERR_UNSUPPORTED, "delta order must be in [0, 7]");
   if (window <= 0 || window >= 1000) return set_error(SNB_ERR_VALUE, "window must be in [1, 999]");
@@ -418,7 +527,14 @@ extern "C" int snb_cmvn_apply_deltas(const float *d_in, int64_t ld_in, int32_t d
   const int halo = a.tap_half[a.order];
   const size_t smem = static_cast<size_t>(kTileRows + 2 * halo) * dim * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (order <= 3 && halo <= kMaxHalo && smem <= 96 * 1024 && dim <= 256) {
+  static const bool no_fixed = getenv("SNB_DELTA_FIXED") && atoi(getenv("SNB_DELTA_FIXED")) == 0;
+  if (window == 2 && (order == 1 || order == 2) && dim <= 80 && !no_fixed) {
+    // (kFixedTile + 8) * 80 floats < 48 KB: no opt-in needed
+    const unsigned ctas = static_cast<unsigned>((total_frames + kFixedTile - 1) / kFixedTile);
+    const size_t smem_fixed = static_cast<size_t>(kFixedTile + 2 * halo) * dim * sizeof(float);
+    if (order == 1) delta_fixed_kernel<1, 2><<<ctas, 256, smem_fixed, st>>>(a);
+    else delta_fixed_kernel<2, 2><<<ctas, 256, smem_fixed, st>>>(a);
+  } else if (order <= 3 && halo <= kMaxHalo && smem <= 96 * 1024 && dim <= 256) {
     const unsigned ctas = static_cast<unsigned>((total_frames + kTileRows - 1) / kTileRows);
     static std::atomic<size_t> cur[4] = {{48 * 1024}, {48 * 1024}, {48 * 1024}, {48 * 1024}};
     auto launch = [&](auto kernel, std::atomic<size_t> *state) -> int {
