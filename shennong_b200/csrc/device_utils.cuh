@@ -120,6 +120,26 @@ __device__ __forceinline__ void gauss_pair_fast(uint32_t key, uint32_t pair, flo
   *g1 = r * s;
 }
 
+// Two dither samples (dither * N(0,1)) for the fused kernel: Box-Muller on the
+// MUFU unit only.  One 32-bit hash per pair: its high half, spliced into the
+// mantissa of 1.0f, gives u1 = (k + 0.5) / 65536 without an int->float
+// conversion; the low half is the angle.  c = -2 ln2 dither^2 folds the change
+// of base of lg2, Box-Muller's -2 and the dither amplitude into one multiply
+// (r = dither sqrt(-2 ln u1) = sqrt(c lg2 u1)).  No operand can be denormal,
+// so the .ftz approximations are used as they are (the generic logf / rsqrtf
+// expansions spend 7 instructions on denormal fix-ups).
+__device__ __forceinline__ float2 dither_pair(uint32_t key, uint32_t pair, float c) {
+  const uint32_t h = hash32(key + pair * 0x9e3779b9u);
+  const float u1 = __uint_as_float(0x3f800040u | ((h >> 9) & 0x007fff80u)) - 1.0f;   // (0, 1)
+  float l, r, sn, cs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * c));
+  const float ang = static_cast<float>(h & 0xffffu) * (6.283185307179586f / 65536.0f);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+  return make_float2(r * cs, r * sn);
+}
+
 // ---- complex helpers ---------------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);

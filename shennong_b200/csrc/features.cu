@@ -525,12 +525,9 @@ fused_features_512_kernel(const FastArgs a) {
         // back only what it wrote, so no synchronisation is needed
         const uint32_t key = frame_noise_key(a.seed, static_cast<uint64_t>(row0 + fidx));
         const int npair = (W + 1) / 2;
-#pragma unroll 1
-        for (int pidx = hl; pidx < npair; pidx += 16) {
-          float g0, g1;
-          gauss_pair_fast(key, pidx, &g0, &g1);
-          s_noise[pidx] = make_float2(dither * g0, dither * g1);
-        }
+        const float c = -1.3862943611198906f * dither * dither;     // -2 ln 2 dither^2
+#pragma unroll 2
+        for (int pidx = hl; pidx < npair; pidx += 16) s_noise[pidx] = dither_pair(key, pidx, c);
       }
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
