@@ -1452,27 +1452,39 @@ static int batch_create_impl(const snb_plan *plan, const int64_t *sample_begin, 
   if (has_tiles && b->ntiles > 0) {
     b->d_tile_first = reinterpret_cast<int64_t *>(d + o_tfirst);
     b->d_tiles = reinterpret_cast<TileDesc *>(d + o_tiles);
-    // expand the tile table on the device, ordered after the upload
-    cudaStream_t s = stream;
-    if (!on_stream) e = upload_stream(&s);
-    if (e == cudaSuccess) {
-      const FeatParams &p = plan->params;
-      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(nutts, 8192));
-      expand_tiles_kernel<<<grid, 64, 0, s>>>(b->d_tiles, b->d_tile_first, b->d_sample_begin, b->d_sample_len,
-                                              b->d_frame_offsets, b->d_utt_mel, nutts, plan->tile_frames, p.S, p.W,
-                                              p.fo.snip_edges);
-      g_launch_count.fetch_add(1, std::memory_order_relaxed);
-      e = cudaGetLastError();
-      if (e == cudaSuccess && !on_stream) e = cudaStreamSynchronize(s);
-    }
-    if (e != cudaSuccess) return fail(set_error(SNB_ERR_CUDA, "tile table expansion failed: %s", cudaGetErrorString(e)));
+    // (expanded on the device by the first launch that needs it, on ITS stream:
+    // a kernel queued here, on the upload stream of a chunked pipeline, would
+    // stall the next chunk's PCM copy behind whatever the SMs are running)
   }
   *out = b;
   return SNB_OK;
 }
 
+// Expands the tile table once, on the stream of the first compute call; later
+// calls on other streams wait for that expansion through an event.
+static int ensure_tiles(const snb_plan *plan, const snb_batch *batch, cudaStream_t stream) {
+  if (!batch->d_tiles || batch->ntiles == 0) return SNB_OK;
+  std::lock_guard<std::mutex> lock(batch->stream_mu);
+  if (!batch->tiles_ready) {
+    const FeatParams &p = plan->params;
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(batch->nutts, 8192));
+    expand_tiles_kernel<<<grid, 64, 0, stream>>>(batch->d_tiles, batch->d_tile_first, batch->d_sample_begin,
+                                                 batch->d_sample_len, batch->d_frame_offsets, batch->d_utt_mel,
+                                                 batch->nutts, plan->tile_frames, p.S, p.W, p.fo.snip_edges);
+    SNB_LAUNCH_CHECK();
+    SNB_CUDA_CHECK(cudaEventCreateWithFlags(&batch->tiles_event, cudaEventDisableTiming));
+    SNB_CUDA_CHECK(cudaEventRecord(batch->tiles_event, stream));
+    batch->tiles_stream = stream;
+    batch->tiles_ready = true;
+  } else if (stream != batch->tiles_stream) {
+    SNB_CUDA_CHECK(cudaStreamWaitEvent(stream, batch->tiles_event, 0));
+  }
+  return SNB_OK;
+}
+
 extern "C" void snb_batch_destroy(snb_batch *b) {
   if (!b) return;
+  if (b->tiles_event) cudaEventDestroy(b->tiles_event);
   if (b->pooled) {
     // recycle the blob once everything queued so far on the streams that used
     // the batch has drained; an unrecordable stream falls back to cudaFree
@@ -1554,6 +1566,10 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
     FastArgs a;
     a.p = p;
     fast_layout(plan, &a.sm);
+    {
+      int rc = ensure_tiles(batch->plan, batch, stream);     // (batch->plan: same framing for a foreign batch)
+      if (rc != SNB_OK) return rc;
+    }
     a.tiles = batch->d_tiles;
     a.ntiles = batch->ntiles;
     a.sample_begin = batch->d_sample_begin;

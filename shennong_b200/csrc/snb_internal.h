@@ -198,6 +198,9 @@ struct snb_batch {
   snb::TileDesc *d_tiles = nullptr;      // fused path: expanded on the device from d_tile_first
   int64_t ntiles = 0;
   int64_t *d_tile_first = nullptr;       // [nutts + 1] first tile of every utterance
+  mutable bool tiles_ready = false;      // guarded by stream_mu (lazy expansion at the first launch)
+  mutable cudaEvent_t tiles_event = nullptr;
+  mutable cudaStream_t tiles_stream = nullptr;
   int32_t *d_utt_mel = nullptr;          // [nutts] mel blob of every utterance
   int32_t *d_mel_blobs = nullptr;  // [nblobs, mel_blob_stride]
   int32_t nblobs = 0;
