@@ -316,3 +316,21 @@ def test_full_size_properties():
     a = lin.process(Audio(half * 2, 16000)).data
     b = lin.process(Audio(half, 16000)).data
     assert np.allclose(a, 4 * b, rtol=1e-5)
+
+
+def test_element_gather_path_without_tma():
+    """The cooperative (non bulk-copy) staging of the fused kernel -- used for
+    unaligned PCM buffers and utterance edges -- on every tile: the golden,
+    ragged-batch and edge-length tests again in a process with SNB_NO_TMA=1"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get('SNB_NO_TMA'):
+        pytest.skip('already inside the SNB_NO_TMA run')
+    env = dict(os.environ, SNB_NO_TMA='1')
+    here = os.path.abspath(__file__)
+    res = subprocess.run(
+        [sys.executable, '-m', 'pytest', here, '-m', 'gpu', '-q', '-x', '-k',
+         'golden or ragged or edge_lengths or plp_py'],
+        env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
