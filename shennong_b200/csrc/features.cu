@@ -529,35 +529,46 @@ fused_features_512_kernel(const FastArgs a) {
 #pragma unroll 2
         for (int pidx = hl; pidx < npair; pidx += 16) s_noise[pidx] = dither_pair(key, pidx, c);
       }
-#pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) {
-        const int i0 = 2 * (16 * n1 + hl);
-        float v0 = 0.0f, v1 = 0.0f;
-        if (n1 >= kN1) {
-          // statically beyond the window: zero padding of the FFT
-        } else if (n1 < nfull) {
-          if (pair_ok) {
-            s16x2_to_f32(*reinterpret_cast<const uint32_t *>(fr + i0), &v0, &v1);
-          } else {
-            v0 = static_cast<float>(fr[i0]);
-            v1 = static_cast<float>(fr[i0 + 1]);
-          }
-          if (dither != 0.0f) {
-            const float2 nz = s_noise[16 * n1 + hl];
-            v0 += nz.x; v1 += nz.y;
-          }
-        } else if (n1 == nfull) {
-          if (i0 < W) v0 = static_cast<float>(fr[i0]);
-          if (i0 + 1 < W) v1 = static_cast<float>(fr[i0 + 1]);
-          if (dither != 0.0f && i0 < W) {
-            const float2 nz = s_noise[16 * n1 + hl];
-            v0 += nz.x;
-            if (i0 + 1 < W) v1 += nz.y;
-          }
-        }
-        xr[n1] = v0; xi[n1] = v1;
-        lsum += v0 + v1;
+      // The usual case -- 32-bit aligned frame, even window length: a lane's two
+      // samples are inside or outside the window together -- gets straight-line
+      // code per dither setting (the tests on pair_ok / dither are hoisted out of
+      // the unrolled loop); anything else takes the element-wise loop.
+#define SNB_LOAD_PAIRS(WITH_NOISE)                                                        \
+      _Pragma("unroll")                                                                   \
+      for (int n1 = 0; n1 < 16; ++n1) {                                                   \
+        const int i0 = 2 * (16 * n1 + hl);                                                \
+        float v0 = 0.0f, v1 = 0.0f;                                                       \
+        if (n1 < kN1 && (n1 < nfull || (n1 == nfull && i0 < W))) {                        \
+          s16x2_to_f32(*reinterpret_cast<const uint32_t *>(fr + i0), &v0, &v1);           \
+          if (WITH_NOISE) {                                                               \
+            const float2 nz = s_noise[16 * n1 + hl];                                      \
+            v0 += nz.x; v1 += nz.y;                                                       \
+          }                                                                               \
+        }                                                                                 \
+        xr[n1] = v0; xi[n1] = v1;                                                         \
+        lsum += v0 + v1;                                                                  \
       }
+      if (pair_ok && (W & 1) == 0) {
+        if (dither != 0.0f) { SNB_LOAD_PAIRS(true) } else { SNB_LOAD_PAIRS(false) }
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+          const int i0 = 2 * (16 * n1 + hl);
+          float v0 = 0.0f, v1 = 0.0f;
+          if (n1 < kN1 && n1 <= nfull) {
+            if (i0 < W) v0 = static_cast<float>(fr[i0]);
+            if (i0 + 1 < W) v1 = static_cast<float>(fr[i0 + 1]);
+            if (dither != 0.0f && i0 < W) {
+              const float2 nz = s_noise[16 * n1 + hl];
+              v0 += nz.x;
+              if (i0 + 1 < W) v1 += nz.y;
+            }
+          }
+          xr[n1] = v0; xi[n1] = v1;
+          lsum += v0 + v1;
+        }
+      }
+#undef SNB_LOAD_PAIRS
       // ---- DC removal (ProcessWindow) ----
       if (p.fo.remove_dc_offset) {
         const float mean = __fdiv_rn(group_sum<16>(lsum), static_cast<float>(W));
