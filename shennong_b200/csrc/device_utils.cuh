@@ -203,5 +203,101 @@ __host__ __device__ __forceinline__ void fft16(float (&re)[16], float (&im)[16])
   }
 }
 
+// ---- packed fp32 pairs (sm_100a add/mul/fma.f32x2 -> SASS FADD2/FMUL2/FFMA2) ----
+// One instruction for two floats held in an aligned 64-bit register pair: the
+// same flop rate as the scalar forms at half the issue slots (measured:
+// tools/microbench/f32x2.cu).  pk / upk are register renames, not moves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
+// the same operations with a compile-time choice between the packed
+// instruction and two scalar ones on the halves (P = false)
+template <bool P> __device__ __forceinline__ f32x2 add2t(f32x2 a, f32x2 b) {
+  if (P) return add2(a, b);
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(a0 + b0, a1 + b1);
+}
+template <bool P> __device__ __forceinline__ f32x2 sub2t(f32x2 a, f32x2 b) {
+  if (P) return sub2(a, b);
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(a0 - b0, a1 - b1);
+}
+template <bool P> __device__ __forceinline__ f32x2 mul2t(f32x2 a, f32x2 b) {
+  if (P) return mul2(a, b);
+  float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(a0 * b0, a1 * b1);
+}
+template <bool P> __device__ __forceinline__ f32x2 fma2t(f32x2 a, f32x2 b, f32x2 c) {
+  if (P) return fma2(a, b, c);
+  float a0, a1, b0, b1, c0, c1; upk(a, a0, a1); upk(b, b0, b1); upk(c, c0, c1);
+  return pk(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+}
+
+// radix-4 butterfly on packed complex values (re, im); pm = (1, -1), mp = (-1, 1).
+// (a1 - a3) * (-i) is formed directly in swapped order by two scalar
+// subtractions, so that the two outputs that need it are one FFMA2 each.
+template <bool P>
+__device__ __forceinline__ void bfly4p(f32x2 a0, f32x2 a1, f32x2 a2, f32x2 a3, f32x2 &y0, f32x2 &y1,
+                                       f32x2 &y2, f32x2 &y3, f32x2 pm, f32x2 mp) {
+  const f32x2 t0 = add2t<P>(a0, a2), t1 = sub2t<P>(a0, a2), t2 = add2t<P>(a1, a3);
+  float a1r, a1i, a3r, a3i;
+  upk(a1, a1r, a1i); upk(a3, a3r, a3i);
+  const float dr = a1r - a3r, di = a1i - a3i;        // d = a1 - a3
+  y0 = add2t<P>(t0, t2); y2 = sub2t<P>(t0, t2);
+  if (P) {
+    const f32x2 dsw = pk(di, dr);                    // formed directly in swapped order
+    y1 = fma2(dsw, pm, t1);                          // t1 - i d
+    y3 = fma2(dsw, mp, t1);                          // t1 + i d
+  } else {
+    float t1r, t1i;
+    upk(t1, t1r, t1i);
+    y1 = pk(t1r + di, t1i - dr);
+    y3 = pk(t1r - di, t1i + dr);
+  }
+}
+
+// fft16 on packed complex values: 104 instructions instead of 160 (40 FADD2 +
+// 16 FFMA2 + 48 scalar), same arithmetic as fft16 (bit-identical results)
+template <bool P>
+__device__ __forceinline__ void fft16p(f32x2 (&x)[16]) {
+  const float C1 = 0.92387953251128674f;  // cos(pi/8)
+  const float S1 = 0.38268343236508977f;  // sin(pi/8)
+  const float R2 = 0.70710678118654752f;  // sqrt(1/2)
+  const f32x2 pm = pk(1.0f, -1.0f), mp = pk(-1.0f, 1.0f);
+  f32x2 b[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2)
+    bfly4p<P>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2], b[n2 * 4], b[n2 * 4 + 1], b[n2 * 4 + 2], b[n2 * 4 + 3], pm, mp);
+  {
+    float r, i;
+    upk(b[5], r, i);  b[5] = pk(r * C1 + i * S1, i * C1 - r * S1);
+    upk(b[6], r, i);  b[6] = pk((r + i) * R2, (i - r) * R2);
+    upk(b[7], r, i);  b[7] = pk(r * S1 + i * C1, i * S1 - r * C1);
+    upk(b[9], r, i);  b[9] = pk((r + i) * R2, (i - r) * R2);
+    upk(b[10], r, i); b[10] = pk(i, -r);
+    upk(b[11], r, i); b[11] = pk((i - r) * R2, -(r + i) * R2);
+    upk(b[13], r, i); b[13] = pk(r * S1 + i * C1, i * S1 - r * C1);
+    upk(b[14], r, i); b[14] = pk((i - r) * R2, -(r + i) * R2);
+    upk(b[15], r, i); b[15] = pk(-(r * C1 + i * S1), -(i * C1 - r * S1));
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+    bfly4p<P>(b[k1], b[4 + k1], b[8 + k1], b[12 + k1], x[k1], x[k1 + 4], x[k1 + 8], x[k1 + 12], pm, mp);
+}
+
 }  // namespace snb
 #endif

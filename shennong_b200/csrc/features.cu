@@ -307,6 +307,18 @@ __device__ __forceinline__ double compress_energy(double e, int mode) {
 // ---------------------------------------------------------------------------
 // fast path: N = 512
 // ---------------------------------------------------------------------------
+// packed fp32 (FADD2/FMUL2/FFMA2) per stage of the fused kernel; compile-time
+// switches so that each stage's gain can be measured separately
+#ifndef SNB_PACK_EW
+#define SNB_PACK_EW 1       // load / DC / energies / window
+#endif
+#ifndef SNB_PACK_FFT
+#define SNB_PACK_FFT 1      // radix-16 butterflies
+#endif
+#ifndef SNB_PACK_UNPACK
+#define SNB_PACK_UNPACK 1   // real-FFT unpack
+#endif
+constexpr bool kPackEw = SNB_PACK_EW != 0, kPackFft = SNB_PACK_FFT != 0, kPackUn = SNB_PACK_UNPACK != 0;
 constexpr int kFastThreads = 256;
 constexpr int kFastGroups = 16;         // half-warps per CTA
 constexpr int kXStride = 17;            // float2 row stride of the transpose buffer
@@ -319,10 +331,11 @@ struct FastSmemLayout {                 // byte offsets into dynamic smem
 // two int16 samples packed in one 32-bit word -> two floats without the
 // quarter-rate I2F: splice each half (biased by 0x8000) into the mantissa of
 // 2^23 and subtract 2^23 + 2^15; exact for every int16 value
-__device__ __forceinline__ void s16x2_to_f32(uint32_t pr, float *v0, float *v1) {
+__device__ __forceinline__ f32x2 s16x2_to_f32x2(uint32_t pr) {
   const uint32_t u = pr ^ 0x80008000u;
-  *v0 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7410)) - 8421376.0f;
-  *v1 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7432)) - 8421376.0f;
+  return sub2t<kPackEw>(pk(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7410)),
+                 __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7432))),
+              pk(8421376.0f, 8421376.0f));
 }
 
 struct FastArgs {
@@ -390,7 +403,6 @@ fused_features_512_kernel(const FastArgs a) {
   const int grp = (tid >> 5) * 2 + (lane >> 4);   // 0..15
   const int gbase = lane & 16;                    // first lane of my group
   float *s_grp = s_grp_all + grp * a.sm.grp_floats;
-  float2 *s_x = reinterpret_cast<float2 *>(s_grp);
 
   const int W = (kW > 0) ? kW : p.W;
   const int S = p.S, B = p.B;
@@ -399,7 +411,7 @@ fused_features_512_kernel(const FastArgs a) {
   const int kind = xo.kind;
 
   // ---- one-time table load ----
-  for (int i = tid; i < 512; i += kFastThreads) s_window[i] = (i < W) ? p.t.window[i] : 0.0f;
+  for (int i = tid; i < 512; i += kFastThreads) s_window[i] = (i < W) ? 0.5f * p.t.window[i] : 0.0f;   // see "window" below
   for (int i = tid; i < 256; i += kFastThreads) {
     const int k1 = i >> 4, l = i & 15;
     s_tw1[i] = p.t.tw_half[(l * k1) & 255];
@@ -511,11 +523,14 @@ fused_features_512_kernel(const FastArgs a) {
       const int fidx = valid ? fl : td.nf - 1;     // idle groups redo the last frame
       const int16_t *fr = pcm_buf + mis + fidx * S;
       const bool pair_ok = pair_ok_static && ((mis & 1) == 0);
-      float xr[16], xi[16];
+      // Lane hl holds the samples (2p, 2p+1), p = 16 n1 + hl, as ONE packed pair
+      // x[n1] = (re, im) of z[p] = s[2p] + i s[2p+1]: every stage that treats the
+      // two halves alike is a single FADD2 / FMUL2 / FFMA2 per register pair.
+      f32x2 x[16];
       // ---- load + int16 -> float (+ dither) ----
       // n1 < nfull: every lane holds two valid samples; n1 == nfull: the
       // ragged tail (W % 32 samples); beyond: zero padding up to 512
-      float lsum = 0.0f;
+      f32x2 lsum2 = pk(0.0f, 0.0f);
       __syncwarp();                 // the previous pass is done with this group's buffer
       float2 *s_noise = reinterpret_cast<float2 *>(s_grp);   // [256] (dither * N(0,1)) pairs
       if (dither != 0.0f) {
@@ -537,16 +552,13 @@ fused_features_512_kernel(const FastArgs a) {
       _Pragma("unroll")                                                                   \
       for (int n1 = 0; n1 < 16; ++n1) {                                                   \
         const int i0 = 2 * (16 * n1 + hl);                                                \
-        float v0 = 0.0f, v1 = 0.0f;                                                       \
+        f32x2 v = pk(0.0f, 0.0f);                                                         \
         if (n1 < kN1 && (n1 < nfull || (n1 == nfull && i0 < W))) {                        \
-          s16x2_to_f32(*reinterpret_cast<const uint32_t *>(fr + i0), &v0, &v1);           \
-          if (WITH_NOISE) {                                                               \
-            const float2 nz = s_noise[16 * n1 + hl];                                      \
-            v0 += nz.x; v1 += nz.y;                                                       \
-          }                                                                               \
+          v = s16x2_to_f32x2(*reinterpret_cast<const uint32_t *>(fr + i0));               \
+          if (WITH_NOISE) v = add2t<kPackEw>(v, *reinterpret_cast<const f32x2 *>(&s_noise[16 * n1 + hl])); \
         }                                                                                 \
-        xr[n1] = v0; xi[n1] = v1;                                                         \
-        lsum += v0 + v1;                                                                  \
+        x[n1] = v;                                                                        \
+        lsum2 = add2t<kPackEw>(lsum2, v);                                                 \
       }
       if (pair_ok && (W & 1) == 0) {
         if (dither != 0.0f) { SNB_LOAD_PAIRS(true) } else { SNB_LOAD_PAIRS(false) }
@@ -564,126 +576,148 @@ fused_features_512_kernel(const FastArgs a) {
               if (i0 + 1 < W) v1 += nz.y;
             }
           }
-          xr[n1] = v0; xi[n1] = v1;
-          lsum += v0 + v1;
+          x[n1] = pk(v0, v1);
+          lsum2 = add2t<kPackEw>(lsum2, x[n1]);
         }
       }
 #undef SNB_LOAD_PAIRS
       // ---- DC removal (ProcessWindow) ----
       if (p.fo.remove_dc_offset) {
-        const float mean = __fdiv_rn(group_sum<16>(lsum), static_cast<float>(W));
+        float l0, l1;
+        upk(lsum2, l0, l1);
+        const float mean = __fdiv_rn(group_sum<16>(l0 + l1), static_cast<float>(W));
+        const f32x2 mean2 = pk(mean, mean);
 #pragma unroll
         for (int n1 = 0; n1 < kN1; ++n1) {
           if (n1 < nfull) {
-            xr[n1] -= mean; xi[n1] -= mean;
+            x[n1] = sub2t<kPackEw>(x[n1], mean2);
           } else if (n1 == nfull) {
             const int i0 = 2 * (16 * n1 + hl);
-            if (i0 < W) xr[n1] -= mean;
-            if (i0 + 1 < W) xi[n1] -= mean;
+            float r, i;
+            upk(x[n1], r, i);
+            if (i0 < W) r -= mean;
+            if (i0 + 1 < W) i -= mean;
+            x[n1] = pk(r, i);
           }
         }
       }
       // ---- raw log-energy / float64 energy ----
       float log_energy = 0.0f;
       if (p.need_raw_energy) {
-        float e = 0.0f;
+        f32x2 e2 = pk(0.0f, 0.0f);
 #pragma unroll
-        for (int n1 = 0; n1 < kN1; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
-        e = group_sum<16>(e);
-        log_energy = logf(fmaxf(e, p.eps_energy));
+        for (int n1 = 0; n1 < kN1; ++n1) e2 = fma2t<kPackEw>(x[n1], x[n1], e2);
+        float e0, e1;
+        upk(e2, e0, e1);
+        log_energy = logf(fmaxf(group_sum<16>(e0 + e1), p.eps_energy));
       }
       // ---- pre-emphasis (needs the ORIGINAL previous sample) ----
       if (p.fo.preemph_coeff != 0.0f) {
         const float c = p.fo.preemph_coeff;
 #pragma unroll
         for (int n1 = kN1 - 1; n1 >= 0; --n1) {
-          const float send = (hl == 15) ? xi[(n1 + 15) & 15] : xi[n1];
+          float r, i, rb, ib;
+          upk(x[n1], r, i);
+          upk(x[(n1 + 15) & 15], rb, ib);
+          const float send = (hl == 15) ? ib : i;
           float prev = __shfl_sync(SNB_FULL_MASK, send, gbase | ((hl + 15) & 15));
-          if (n1 == 0 && hl == 0) prev = xr[0];
-          xi[n1] = fmaf(-c, xr[n1], xi[n1]);
-          xr[n1] = fmaf(-c, prev, xr[n1]);
+          if (n1 == 0 && hl == 0) prev = r;
+          x[n1] = pk(fmaf(-c, prev, r), fmaf(-c, r, i));
         }
       }
-      // ---- window (zero beyond W: also clears pre-emphasis spill) ----
+      // ---- window (zero beyond W: also clears pre-emphasis spill).  The table
+      //      holds HALF the window: the real-FFT unpack then needs no 1/4 ----
 #pragma unroll
-      for (int n1 = 0; n1 < kN1; ++n1) {
-        const float2 w = *reinterpret_cast<const float2 *>(s_window + 2 * (16 * n1 + hl));
-        xr[n1] *= w.x; xi[n1] *= w.y;
-      }
+      for (int n1 = 0; n1 < kN1; ++n1)
+        x[n1] = mul2t<kPackEw>(x[n1], *reinterpret_cast<const f32x2 *>(s_window + 2 * (16 * n1 + hl)));
       if (kind == SNB_FEAT_ENERGY) {
         double e = 0.0;
 #pragma unroll
-        for (int n1 = 0; n1 < kN1; ++n1)
-          e += static_cast<double>(xr[n1]) * xr[n1] + static_cast<double>(xi[n1]) * xi[n1];
-        e = group_sum_f64<16>(e);
+        for (int n1 = 0; n1 < kN1; ++n1) {
+          float r, i;
+          upk(x[n1], r, i);
+          e += static_cast<double>(r) * r + static_cast<double>(i) * i;
+        }
+        e = 4.0 * group_sum_f64<16>(e);
         if (valid && hl == 0)
           reinterpret_cast<double *>(a.out)[(row0 + fl) * a.ld_out] =
               compress_energy(e, xo.energy_compression);
         break;
       }
       if (p.need_post_energy) {
-        float e = 0.0f;
+        f32x2 e2 = pk(0.0f, 0.0f);
 #pragma unroll
-        for (int n1 = 0; n1 < kN1; ++n1) e = fmaf(xr[n1], xr[n1], fmaf(xi[n1], xi[n1], e));
-        e = group_sum<16>(e);
-        log_energy = logf(fmaxf(e, p.eps_energy));
+        for (int n1 = 0; n1 < kN1; ++n1) e2 = fma2t<kPackEw>(x[n1], x[n1], e2);
+        float e0, e1;
+        upk(e2, e0, e1);
+        log_energy = logf(fmaxf(4.0f * group_sum<16>(e0 + e1), p.eps_energy));
       }
 
       // ---- 256-point complex FFT = 16 x 16 ----
       // (a 2-trip loop that is NOT unrolled: one copy of the radix-16 code)
+      f32x2 *s_x = reinterpret_cast<f32x2 *>(s_grp);
 #pragma unroll 1
       for (int fft_pass = 0; fft_pass < 2; ++fft_pass) {
-        fft16(xr, xi);                  // pass 0: over n1 (lane = n2); pass 1: over n2 -> Z[hl + 16 k2]
+        fft16p<kPackFft>(x);                  // pass 0: over n1 (lane = n2); pass 1: over n2 -> Z[hl + 16 k2]
         if (fft_pass == 0) {
 #pragma unroll
           for (int k1 = 1; k1 < 16; ++k1) {
             const float2 w = s_tw1[k1 * 16 + hl];
-            const float r = xr[k1], i = xi[k1];
-            xr[k1] = r * w.x - i * w.y;
-            xi[k1] = r * w.y + i * w.x;
+            float r, i;
+            upk(x[k1], r, i);
+            x[k1] = pk(r * w.x - i * w.y, r * w.y + i * w.x);
           }
           __syncwarp();                 // every lane is done reading its noise
 #pragma unroll
-          for (int k1 = 0; k1 < 16; ++k1) s_x[k1 * kXStride + hl] = make_float2(xr[k1], xi[k1]);
+          for (int k1 = 0; k1 < 16; ++k1) s_x[k1 * kXStride + hl] = x[k1];
           __syncwarp();
 #pragma unroll
-          for (int n2 = 0; n2 < 16; ++n2) {
-            const float2 v = s_x[hl * kXStride + n2];
-            xr[n2] = v.x; xi[n2] = v.y;
-          }
+          for (int n2 = 0; n2 < 16; ++n2) x[n2] = s_x[hl * kXStride + n2];
         }
       }
       __syncwarp();                                   // transpose buffer free -> reuse as P
       float *P = s_grp;
       // ---- real-FFT unpack: pairs (k, 256-k), k = hl + 16 k2, k2 < 8 ----
+      // With Z = FFT of the half-scaled frame: X[k] = E + W^k O, X[256-k] =
+      // conj(E - W^k O), E = Z[k] + conj Z[256-k], O = -i (Z[k] - conj Z[256-k]).
       // P in the padded layout of pidx<16>: k -> 24 k2 + pk, 256-k -> 24 (15-k2) + pq
       const int partner = gbase | ((16 - hl) & 15);
-      const int pk = kPStride * (hl >> 3) + (hl & 7);
-      const int pq = (hl == 0) ? 2 * kPStride : kPStride * ((16 - hl) >> 3) + ((16 - hl) & 7);
+      const int pko = kPStride * (hl >> 3) + (hl & 7);
+      const int pqo = (hl == 0) ? 2 * kPStride : kPStride * ((16 - hl) >> 3) + ((16 - hl) & 7);
+      const f32x2 pm = pk(1.0f, -1.0f), mp = pk(-1.0f, 1.0f);
 #pragma unroll
       for (int k2 = 0; k2 < 8; ++k2) {
-        const float sr = (hl == 0) ? xr[(16 - k2) & 15] : xr[15 - k2];
-        const float si = (hl == 0) ? xi[(16 - k2) & 15] : xi[15 - k2];
-        const float cr = __shfl_sync(SNB_FULL_MASK, sr, partner);   // Z[256-k]
-        const float ci = __shfl_sync(SNB_FULL_MASK, si, partner);
-        const float ar = xr[k2], ai = xi[k2];
+        float sr, si, qr, qi;
+        upk(x[15 - k2], sr, si);
+        upk(x[(16 - k2) & 15], qr, qi);
+        const float cr = __shfl_sync(SNB_FULL_MASK, (hl == 0) ? qr : sr, partner);   // Z[256-k]
+        const float ci = __shfl_sync(SNB_FULL_MASK, (hl == 0) ? qi : si, partner);
+        const f32x2 c = pk(cr, ci), z = x[k2];
         const int k = hl + 16 * k2;
         if (k == 0) {
+          float ar, ai;
+          upk(z, ar, ai);
           const float s0 = ar + ai, d0 = ar - ai;
-          P[0] = s0 * s0;
-          P[pidx<16>(256)] = d0 * d0;
+          P[0] = (s0 + s0) * (s0 + s0);
+          P[pidx<16>(256)] = (d0 + d0) * (d0 + d0);
         } else {
           const float2 w = s_tw2[k2 * 16 + hl];
-          const float er = ar + cr, ei = ai - ci;      // 2E
-          const float u = ai + ci, v = cr - ar;        // -i * (Z - conj Zp)
-          const float orr = w.x * u - w.y * v, oi = w.x * v + w.y * u;   // 2 W O
-          const float x1r = er + orr, x1i = ei + oi;
-          const float x2r = er - orr, x2i = ei - oi;
-          P[2 * kPStride * k2 + pk] = 0.25f * (x1r * x1r + x1i * x1i);
-          P[2 * kPStride * (15 - k2) + pq] = 0.25f * (x2r * x2r + x2i * x2i);
+          const f32x2 e = fma2t<kPackUn>(c, pm, z);    // (ar + cr, ai - ci)
+          float u, v;
+          upk(fma2t<kPackUn>(z, mp, c), v, u);         // (cr - ar, ci + ai)
+          const f32x2 o = pk(w.x * u - w.y * v, w.x * v + w.y * u);   // W O
+          float x1r, x1i, x2r, x2i;
+          upk(add2t<kPackUn>(e, o), x1r, x1i);
+          upk(sub2t<kPackUn>(e, o), x2r, x2i);
+          P[2 * kPStride * k2 + pko] = fmaf(x1r, x1r, x1i * x1i);
+          P[2 * kPStride * (15 - k2) + pqo] = fmaf(x2r, x2r, x2i * x2i);
         }
       }
-      if (hl == 0) P[pidx<16>(128)] = xr[8] * xr[8] + xi[8] * xi[8];
+      if (hl == 0) {
+        float r8, i8;
+        upk(x[8], r8, i8);
+        P[pidx<16>(128)] = 4.0f * (r8 * r8 + i8 * i8);
+      }
       __syncwarp();
 
       float *out_row = reinterpret_cast<float *>(a.out) + (row0 + fl) * a.ld_out;
