@@ -41,9 +41,19 @@ FRAMES_PER_UTT = 998
 BYTES_PER_FRAME_KERNEL = 320 + 4 * 13     # PCM read once + 13 cepstra written
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_features_512_kernel
 # launch over 9.98e6 frames (ncu capture of `bench.py --steps 2 --warmup 2`,
-# profiles/r01_ncu_traffic_fused_features_512_final.csv): 3 217 049 088 +
-# 509 941 760 B = 373.4 B/frame, i.e. 1.003 x the algorithmic bytes
-NCU_TRAFFIC_BYTES_PER_FRAME = (3217049088 + 509941760) / 9980000.0
+# profiles/r01_final_ncu_traffic_fused_features_512.csv): 3 242 790 912 +
+# 512 223 488 B = 376.3 B/frame, i.e. 1.011 x the algorithmic bytes (the
+# extra 2 B/frame is the 32-byte tile descriptor per 16 frames)
+NCU_TRAFFIC_BYTES_PER_FRAME = (3242790912 + 512223488) / 9980000.0
+TRAFFIC_SOURCE = ('ncu capture of this launch shape, '
+                  'profiles/r01_final_ncu_traffic_fused_features_512.csv')
+# what actually bounds the dominant kernel (ncu --set full of the same kernel on
+# 2 000 utterances, profiles/r01_final_ncu_fused_features_512_dither*.txt)
+NCU_LIMITS = {
+    'source': 'profiles/r01_final_ncu_fused_features_512_dither1.0.txt',
+    'issue_slots_busy_pct': 72.9, 'smem_data_pipe_busy_pct': 64.0,
+    'warp_instructions_per_frame': 936, 'smem_wavefronts_per_frame': 215,
+    'dram_throughput_pct': 4.0}
 BYTES_PER_FRAME_PIPELINE = 320 + 4 * 39   # + delta/cmvn output
 FLOPS_PER_FRAME = 17000
 
@@ -172,12 +182,18 @@ def cpu_baseline(pcm_host, nutts_avail, dither, budget_s=12.0):
     dt, frames = run(probe)
     rate = frames / dt
     n = int(min(nutts_avail, max(probe, rate * budget_s / FRAMES_PER_UTT)))
-    dt, frames = run(n)
+    # passes over the sample until about budget_s of CPU work has been timed
+    reps = int(max(1, min(64, round(budget_s * rate / (n * FRAMES_PER_UTT)))))
+    dt, frames = 0.0, 0
+    for _ in range(reps):
+        d, f = run(n)
+        dt += d
+        frames += f
     return {'value': frames / dt, 'unit': 'frames/s', 'cores': cores,
             'kind': 'port',
-            'sample': f'{n} of the synthetic 10 s utterances '
-                      f'({frames} frames) in {dt:.2f} s, C oracle, OpenMP '
-                      f'over utterances'}, n, dt
+            'sample': f'{reps} pass(es) over {n} of the synthetic 10 s '
+                      f'utterances ({frames} frames) in {dt:.2f} s, C oracle, '
+                      f'OpenMP over utterances'}, n, dt
 
 
 def main():
@@ -371,13 +387,14 @@ def main():
         'achieved': feat_gbs, 'peak': peak, 'unit': 'GB/s',
         'frac': feat_gbs / peak,
         'traffic': int(total_frames * NCU_TRAFFIC_BYTES_PER_FRAME),
-        'traffic_source': 'ncu capture of this launch shape, '
-                          'profiles/r01_ncu_traffic_fused_features_512_final.csv',
+        'traffic_source': TRAFFIC_SOURCE,
         'peak_source': peak_src,
         'algorithmic_bytes_per_launch': int(total_frames * BYTES_PER_FRAME_KERNEL),
         'kernel_ms': ms_feat,
-        'note': ('the chain is fp32/SFU-bound (~17 kflop/frame, AI ~45 flop/B): '
-                 'see fp32_tflops'),
+        'note': ('the chain is instruction-issue / shared-memory bound (~17 '
+                 'kflop/frame, AI ~45 flop/B), not HBM bound: see limits and '
+                 'fp32_tflops'),
+        'limits': NCU_LIMITS,
         'fp32_tflops': total_frames * FLOPS_PER_FRAME / (ms_feat * 1e-3) / 1e12,
         'pipeline_gbs': total_frames * BYTES_PER_FRAME_PIPELINE
         / (ms_per_step * 1e-3) / 1e9,

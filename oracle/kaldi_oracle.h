@@ -14,8 +14,9 @@
  * the reference's own call sites and its in-tree Python restatement of
  * ExtractWindow/ProcessWindow/PlpComputer (shennong/processor/plp.py:149-260,
  * 510-626).  Parity pinning: see oracle/README.md (fbank/mfcc/spectrogram are
- * pinned against torchaudio.compliance.kaldi golden vectors; PLP and pitch are
- * "parity unpinned").
+ * pinned against torchaudio.compliance.kaldi golden vectors; PLP, RASTA-PLP
+ * and energy against the outputs of the reference's own plp.py / energy.py run
+ * over a pykaldi shim; Kaldi pitch is "parity unpinned").
  */
 #ifndef KALDI_ORACLE_H_
 #define KALDI_ORACLE_H_

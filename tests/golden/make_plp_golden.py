@@ -41,6 +41,7 @@ _pkg = types.ModuleType('shennong.processor')
 _pkg.__path__ = ['/root/reference/shennong/processor']
 sys.modules['shennong.processor'] = _pkg
 from shennong.processor.plp import PlpProcessor  # noqa: E402
+from shennong.processor.energy import EnergyProcessor  # noqa: E402
 
 WAV = '/root/reference/test/data/test.wav'
 
@@ -67,6 +68,17 @@ CASES = [
 ]
 
 
+# EnergyProcessor is a Python frame loop as well (energy.py:153-186)
+ENERGY_CASES = [
+    ('energy_default', {}),
+    ('energy_sqrt', {'compression': 'sqrt'}),
+    ('energy_off_not_raw', {'compression': 'off', 'raw_energy': False}),
+    ('energy_hamming_not_raw', {'raw_energy': False, 'window_type': 'hamming'}),
+    ('energy_nosnip', {'snip_edges': False}),
+    ('energy_shift20_len50_nodc', {'frame_shift': 0.02, 'frame_length': 0.05, 'remove_dc_offset': False}),
+]
+
+
 def main():
     rate, pcm = scipy.io.wavfile.read(WAV)
     assert rate == 16000 and pcm.dtype == np.int16 and pcm.ndim == 1
@@ -78,7 +90,15 @@ def main():
         feats = proc.process(audio, vtln_warp=warp)
         out[name] = np.asarray(feats.data, dtype=np.float32)
         out[name + '.times'] = np.asarray(feats.times, dtype=np.float64)
-        meta[name] = {'kwargs': kwargs, 'vtln_warp': warp, 'shape': list(feats.shape)}
+        meta[name] = {'kind': 'plp', 'kwargs': kwargs, 'vtln_warp': warp, 'shape': list(feats.shape)}
+        print('%-24s %s' % (name, feats.shape))
+    for name, kwargs in ENERGY_CASES:
+        proc = EnergyProcessor(sample_rate=rate, dither=0.0, **kwargs)
+        feats = proc.process(audio)
+        assert feats.data.dtype == np.float64
+        out[name] = np.asarray(feats.data, dtype=np.float64)
+        out[name + '.times'] = np.asarray(feats.times, dtype=np.float64)
+        meta[name] = {'kind': 'energy', 'kwargs': kwargs, 'shape': list(feats.shape)}
         print('%-24s %s' % (name, feats.shape))
     out['meta'] = np.array(json.dumps(meta))
     np.savez_compressed(os.path.join(HERE, 'plp_reference_shim.npz'), **out)

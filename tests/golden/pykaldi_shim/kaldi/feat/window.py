@@ -96,3 +96,9 @@ class FeatureWindowFunction:
                 raise ValueError(t)
             w[i] = v
         return cls(Vector._view(w))
+
+
+def extract_window(sample_offset, wave, frame, opts, window_function, window, log_energy_pre_window=None):
+    """ExtractWindow: delegated to the reference's own Python restatement (plp.py:212-260)"""
+    from shennong.processor.plp import _extract_window
+    _extract_window(sample_offset, wave, frame, opts, window_function, window, False)
