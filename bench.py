@@ -68,6 +68,8 @@ def parse_args():
                     help='utterances per GPU')
     ap.add_argument('--dither', type=float, default=1.0)
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--chunk-utts', type=int, default=512,
+                    help='utterances per chunk of the host pipeline (e2e)')
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
 
@@ -353,13 +355,15 @@ def main():
         del scratch
         nrep = max(2, min(args.steps, 5))
         for _ in range(2):                                           # warm-up
-            pipe.run_host(host_pcm, starts, lengths, out_host=out_host)
+            pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
+                          chunk_utts=args.chunk_utts)
         barrier()
         rep_ms = []
         t_e0 = time.perf_counter()
         for _ in range(nrep):
             t_r = time.perf_counter()
-            pipe.run_host(host_pcm, starts, lengths, out_host=out_host)
+            pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
+                          chunk_utts=args.chunk_utts)
             rep_ms.append((time.perf_counter() - t_r) * 1e3)
         barrier()
         dt = (time.perf_counter() - t_e0) / nrep
@@ -372,7 +376,8 @@ def main():
                'd2h_bytes_per_step': int(total_frames * 39 * 4),
                'ms_per_step': dt * 1e3,
                'ms_each_step': [round(t, 2) for t in rep_ms],
-               'api': 'FusedPipeline.run_host (chunked H2D/compute/D2H)',
+               'api': 'FusedPipeline.run_host (chunked H2D/compute/D2H, '
+                      f'{args.chunk_utts} utterances per chunk)',
                'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs}
 
     if rank != 0:

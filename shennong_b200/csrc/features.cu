@@ -1643,11 +1643,7 @@ static int compute_features_impl(const snb_plan *plan, const snb_batch *batch, c
     };
     int rc;
     static const bool no_w400 = getenv("SNB_FUSED_W400") && atoi(getenv("SNB_FUSED_W400")) == 0;
-    static const bool occ2 = getenv("SNB_FUSED_OCC") && atoi(getenv("SNB_FUSED_OCC")) == 2;
-    static std::atomic<size_t> smem2{0};
-    if (p.W == 400 && occ2)
-      rc = launch(fused_features_512_kernel<2, 400>, &smem2);      // experiment: 128 registers
-    else if (p.W == 400 && !no_w400)
+    if (p.W == 400 && !no_w400)
       rc = (plan->fused_occ == 4) ? launch(fused_features_512_kernel<4, 400>, &g_fast_smem4_w400)
                                   : launch(fused_features_512_kernel<3, 400>, &g_fast_smem_w400);
     else
