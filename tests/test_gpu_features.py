@@ -87,6 +87,13 @@ def test_plp_vs_reference_plp_py(golden_plp):
     ('plp', {'lpc_order': 10, 'num_ceps': 8, 'cepstral_scale': 2.0,
              'compress_factor': 0.5, 'num_bins': 30}),
     ('plp', {'snip_edges': False, 'raw_energy': False}),
+    # odd window length (321 samples) and odd shift (161): the element-wise
+    # load path and the ragged last register of the fused kernel
+    ('mfcc', {'frame_length': 0.0200625, 'frame_shift': 0.0100625}),
+    ('filterbank', {'frame_length': 0.0200625, 'remove_dc_offset': False}),
+    # 100 ms shift: tiles of 8 frames (half of the lane groups idle)
+    ('mfcc', {'frame_shift': 0.1}),
+    ('spectrogram', {'frame_shift': 0.05, 'snip_edges': False}),
 ])
 def test_fast_path_vs_oracle(pcm, kind, kwargs):
     feats = run(kind, pcm, **kwargs)
@@ -341,3 +348,35 @@ def test_element_gather_path_without_tma():
          'golden or ragged or edge_lengths or plp_py'],
         env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_unaligned_utterance_offsets():
+    """The C ABI takes any sample_begin: utterances packed at odd / non 16-byte
+    offsets go through the misaligned bulk-copy and the element-wise load
+    paths of the fused kernel and must give the same rows"""
+    import torch
+    from shennong_b200 import engine
+    lengths = [22713, 5000, 16001, 48000, 401]
+    sigs = [synth_utterance(10 + i, n) for i, n in enumerate(lengths)]
+    gaps = [3, 1, 7, 2, 5]                    # odd and even misalignments
+    starts, pos = [], 0
+    for n, gap in zip(lengths, gaps):
+        pos += gap
+        starts.append(pos)
+        pos += n
+    buf = np.zeros(pos + 64, dtype=np.int16)
+    for s, start in zip(sigs, starts):
+        buf[start:start + len(s)] = s
+    dev = torch.from_numpy(buf).cuda()
+    for proc in (MfccProcessor(dither=0), FilterbankProcessor(dither=0, num_bins=40),
+                 MfccProcessor(dither=0, snip_edges=False)):
+        plan = engine.feature_plan(
+            proc._frame_opts(), proc._mel_opts(), proc._feat_opts())
+        packed = engine.PackedAudio.from_packed(
+            None, np.array(starts), np.array(lengths), dev=dev)
+        batch = engine.Batch(plan, packed)
+        out = engine.to_host(engine.compute_features(plan, batch))
+        offs = batch.frame_offsets
+        for i, sig in enumerate(sigs):
+            single = proc.process(Audio(sig, 16000)).data
+            assert np.array_equal(out[offs[i]:offs[i + 1]], single), i
