@@ -96,8 +96,8 @@ __device__ __forceinline__ void gauss_pair(uint64_t seed, uint64_t frame,
   *g1 = r * s;
 }
 
-// cheaper variant for the fused fast path: one 32-bit hash per PAIR of samples
-// (16 bits per uniform: |g| <= 4.86), MUFU-only Box-Muller
+// fused fast path: one 32-bit hash per PAIR of samples (16 bits per uniform:
+// |g| <= 4.86), see dither_pair
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du;
   x ^= x >> 15; x *= 0x846ca68bu;
@@ -107,17 +107,6 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 __device__ __forceinline__ uint32_t frame_noise_key(uint64_t seed, uint64_t frame) {
   const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
   return hash32(hash32(static_cast<uint32_t>(frame) ^ lo) + static_cast<uint32_t>(frame >> 32)) ^ hi;
-}
-__device__ __forceinline__ void gauss_pair_fast(uint32_t key, uint32_t pair, float *g0, float *g1) {
-  const uint32_t h = hash32(key + pair * 0x9e3779b9u);
-  const float u1 = (static_cast<float>(h >> 16) + 0.5f) * (1.0f / 65536.0f);   // (0,1)
-  const float u2 = static_cast<float>(h & 0xffffu) * (1.0f / 65536.0f);        // [0,1)
-  const float t = -2.0f * __logf(u1);          // > 0
-  const float r = t * rsqrtf(t);               // sqrt(t)
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  *g0 = r * c;
-  *g1 = r * s;
 }
 
 // Two dither samples (dither * N(0,1)) for the fused kernel: Box-Muller on the
@@ -138,69 +127,6 @@ __device__ __forceinline__ float2 dither_pair(uint32_t key, uint32_t pair, float
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
   return make_float2(r * cs, r * sn);
-}
-
-// ---- complex helpers ---------------------------------------------------------
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// in-register 16-point DFT (forward, e^{-2 pi i nk/16}), radix 4x4,
-// natural-order output.  ~168 flops.
-__host__ __device__ __forceinline__ void fft16(float (&re)[16], float (&im)[16]) {
-  const float C1 = 0.92387953251128674f;  // cos(pi/8)
-  const float S1 = 0.38268343236508977f;  // sin(pi/8)
-  const float R2 = 0.70710678118654752f;  // sqrt(1/2)
-  float br[16], bi[16];
-  // stage 1: four 4-point DFTs over n1 (stride 4), results b[n2][k1]
-#pragma unroll
-  for (int n2 = 0; n2 < 4; ++n2) {
-    const float ar0 = re[n2], ai0 = im[n2];
-    const float ar1 = re[4 + n2], ai1 = im[4 + n2];
-    const float ar2 = re[8 + n2], ai2 = im[8 + n2];
-    const float ar3 = re[12 + n2], ai3 = im[12 + n2];
-    const float t0r = ar0 + ar2, t0i = ai0 + ai2;
-    const float t1r = ar0 - ar2, t1i = ai0 - ai2;
-    const float t2r = ar1 + ar3, t2i = ai1 + ai3;
-    // (a1 - a3) * (-i) = (im, -re)
-    const float t3r = ai1 - ai3, t3i = -(ar1 - ar3);
-    br[n2 * 4 + 0] = t0r + t2r; bi[n2 * 4 + 0] = t0i + t2i;
-    br[n2 * 4 + 1] = t1r + t3r; bi[n2 * 4 + 1] = t1i + t3i;
-    br[n2 * 4 + 2] = t0r - t2r; bi[n2 * 4 + 2] = t0i - t2i;
-    br[n2 * 4 + 3] = t1r - t3r; bi[n2 * 4 + 3] = t1i - t3i;
-  }
-  // twiddles W16^{n2 k1}
-  // n2=1: k1=1 W1, k1=2 W2, k1=3 W3
-  {
-    float r, i;
-    r = br[5]; i = bi[5]; br[5] = r * C1 + i * S1; bi[5] = i * C1 - r * S1;          // W1 = (C1,-S1)
-    r = br[6]; i = bi[6]; br[6] = (r + i) * R2;    bi[6] = (i - r) * R2;             // W2 = (R2,-R2)
-    r = br[7]; i = bi[7]; br[7] = r * S1 + i * C1; bi[7] = i * S1 - r * C1;          // W3 = (S1,-C1)
-    // n2=2: k1=1 W2, k1=2 W4=-i, k1=3 W6 = (-R2,-R2)
-    r = br[9]; i = bi[9]; br[9] = (r + i) * R2;    bi[9] = (i - r) * R2;
-    r = br[10]; i = bi[10]; br[10] = i;            bi[10] = -r;
-    r = br[11]; i = bi[11]; br[11] = (i - r) * R2; bi[11] = -(r + i) * R2;
-    // n2=3: k1=1 W3, k1=2 W6, k1=3 W9 = -W1 = (-C1, S1)
-    r = br[13]; i = bi[13]; br[13] = r * S1 + i * C1; bi[13] = i * S1 - r * C1;
-    r = br[14]; i = bi[14]; br[14] = (i - r) * R2;    bi[14] = -(r + i) * R2;
-    r = br[15]; i = bi[15]; br[15] = -(r * C1 + i * S1); bi[15] = -(i * C1 - r * S1);
-  }
-  // stage 2: four 4-point DFTs over n2 for each k1; out[k1 + 4 k2]
-#pragma unroll
-  for (int k1 = 0; k1 < 4; ++k1) {
-    const float ar0 = br[k1], ai0 = bi[k1];
-    const float ar1 = br[4 + k1], ai1 = bi[4 + k1];
-    const float ar2 = br[8 + k1], ai2 = bi[8 + k1];
-    const float ar3 = br[12 + k1], ai3 = bi[12 + k1];
-    const float t0r = ar0 + ar2, t0i = ai0 + ai2;
-    const float t1r = ar0 - ar2, t1i = ai0 - ai2;
-    const float t2r = ar1 + ar3, t2i = ai1 + ai3;
-    const float t3r = ai1 - ai3, t3i = -(ar1 - ar3);
-    re[k1 + 0] = t0r + t2r;  im[k1 + 0] = t0i + t2i;
-    re[k1 + 4] = t1r + t3r;  im[k1 + 4] = t1i + t3i;
-    re[k1 + 8] = t0r - t2r;  im[k1 + 8] = t0i - t2i;
-    re[k1 + 12] = t1r - t3r; im[k1 + 12] = t1i - t3i;
-  }
 }
 
 // ---- packed fp32 pairs (sm_100a add/mul/fma.f32x2 -> SASS FADD2/FMUL2/FFMA2) ----
@@ -270,8 +196,10 @@ __device__ __forceinline__ void bfly4p(f32x2 a0, f32x2 a1, f32x2 a2, f32x2 a3, f
   }
 }
 
-// fft16 on packed complex values: 104 instructions instead of 160 (40 FADD2 +
-// 16 FFMA2 + 48 scalar), same arithmetic as fft16 (bit-identical results)
+// in-register 16-point DFT (forward, e^{-2 pi i nk/16}), radix 4x4,
+// natural-order output, on packed complex values: 104 instructions (40 FADD2 +
+// 16 FFMA2 + 48 scalar) instead of the 160 of the scalar form (P = false),
+// bit-identical results
 template <bool P>
 __device__ __forceinline__ void fft16p(f32x2 (&x)[16]) {
   const float C1 = 0.92387953251128674f;  // cos(pi/8)
