@@ -159,7 +159,10 @@ int32_t snb_plan_uses_fast_path(const snb_plan *plan);
 /* ---- ragged batches ----------------------------------------------------- */
 /* sample_begin / sample_len: HOST int64[nutts], utterance u is
  * pcm[sample_begin[u] .. sample_begin[u] + sample_len[u]) of the packed int16
- * buffer (begins that are multiples of 8 samples enable the TMA staging path).
+ * buffer.  Any begin works: the fused kernel bulk-copies (TMA) the 16-byte
+ * aligned piece that covers a tile whenever the buffer itself is 16-byte
+ * aligned; even begins keep the paired 32-bit sample loads.  The per-tile
+ * table is expanded on the device by the first compute call, on its stream.
  * vtln_warps: HOST float[nutts] or NULL (all 1.0) -- the vtln_warp argument
  * of MelFeaturesProcessor.process (processor/base.py:376-406). */
 int snb_batch_create(const snb_plan *plan, const int64_t *sample_begin,
