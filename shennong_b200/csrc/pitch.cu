@@ -603,21 +603,22 @@ __host__ __device__ inline WarpSmem warp_smem_layout(int full_len, int nm, int n
 }
 
 __host__ __device__ inline int warp_shared_floats(int ns, int nw_max) {
-  return ((2 * ns + ns * (nw_max | 1) + ns) + 3) / 4 * 4;     // pen, lags, up_w (odd row stride), up_first
+  return ((3 * ns + ns * (nw_max | 1) + ns) + 3) / 4 * 4;     // pen (mirrored), lags, up_w (odd row stride), up_first
 }
 
 // first argmin over j in [jlo, jhi] of pen[|i-j|] + prev[j], by the whole warp.
 // Costs are non-negative floats (pen >= 0, prev >= 0): their bit patterns order
 // like integers, so the warp minimum is one REDUX (then one more for the
 // smallest j among the lanes that hold it: the first minimum).
-__device__ __forceinline__ int coop_scan(const float *s_pen, const float *w_prev, int i, int jlo, int jhi,
+// s_penc is the centre of the mirrored penalty table: s_penc[d] = pen[|d|].
+__device__ __forceinline__ int coop_scan(const float *s_penc, const float *w_prev, int i, int jlo, int jhi,
                                          int lane) {
   int best = 0x7f7fffff;          // FLT_MAX
   int bj = 0x7fffffff;
-#pragma unroll 1
+  const float *pq = s_penc - i;
+#pragma unroll 2
   for (int j = jlo + lane; j <= jhi; j += 32) {
-    const int d = j > i ? j - i : i - j;
-    const int c = __float_as_int(__fadd_rn(s_pen[d], w_prev[j]));
+    const int c = __float_as_int(__fadd_rn(pq[j], w_prev[j]));
     if (c < best) { best = c; bj = j; }
   }
   const int m = __reduce_min_sync(SNB_FULL_MASK, best);
@@ -642,12 +643,14 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
   const int nw = NWC > 0 ? NWC : a.up_nw_max;
   const int nwp = nw | 1;                                     // odd row stride: conflict-free
   // ---- CTA-shared tables ----
-  float *s_pen = reinterpret_cast<float *>(smem_raw);
-  float *s_lags = s_pen + ns;
+  // penalty table mirrored around s_pen: s_pen[d] = pen[|d|], d in (-ns, ns):
+  // the scans index it with the signed state distance, no absolute value
+  float *s_pen = reinterpret_cast<float *>(smem_raw) + (ns - 1);
+  float *s_lags = reinterpret_cast<float *>(smem_raw) + 2 * ns;
   float *s_upw = s_lags + ns;                                 // [ns][nwp]
   int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + ns * nwp);
   for (int i = tid; i < ns; i += blockDim.x) {
-    s_pen[i] = a.pen[i]; s_lags[i] = a.lags[i];
+    s_pen[i] = a.pen[i]; s_pen[-i] = a.pen[i]; s_lags[i] = a.lags[i];
     s_upfirst[i] = min(max(a.up_first[i], 0), nm - 1);         // (a state without taps has zero weights)
   }
   for (int i = tid; i < ns * nw; i += blockDim.x) s_upw[(i / nw) * nwp + i % nw] = a.up_w[i];
@@ -848,15 +851,15 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
           int bj = jlo;
           if (jhi > jlo && jhi - jlo < T) {
             float best = FLT_MAX;
-            const float *pp = w_prev + jlo;
-            int d = jlo - i, bd = d;
-#pragma unroll 1
+            const float *pp = w_prev + jlo, *pq = s_pen + (jlo - i);
+            int bn = 0;
+#pragma unroll 2
             for (int n = jhi - jlo; n >= 0; --n) {
-              const float c = __fadd_rn(s_pen[d < 0 ? -d : d], *pp);
-              if (c < best) { best = c; bd = d; }
-              ++pp; ++d;
+              const float c = __fadd_rn(*pq, *pp);
+              if (c < best) { best = c; bn = n; }
+              ++pp; ++pq;
             }
-            bj = i + bd;
+            bj = jhi - bn;
           }
 #pragma unroll 1
           while (longm) {
@@ -876,8 +879,7 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
       float lmin = FLT_MAX;
       for (int i = lane; i < ns; i += 32) {
         const int bj = w_bp[bp_slot(i)];
-        const int d = bj > i ? bj - i : i - bj;
-        const float v = __fadd_rn(__fadd_rn(s_pen[d], w_prev[bj]), w_cost[i]);
+        const float v = __fadd_rn(__fadd_rn(s_pen[bj - i], w_prev[bj]), w_cost[i]);
         bp[f * ns + i] = static_cast<int16_t>(bj);
         w_cost[i] = v;
         lmin = fminf(lmin, v);
