@@ -380,6 +380,31 @@ def main():
                       f'{args.chunk_utts} utterances per chunk)',
                'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs}
 
+    # ---- collection (outside the step): NCCL all-gather of the feature blocks --
+    gather = None
+    if world > 1:
+        from shennong_b200.distributed import gather_rows
+        full, _ = gather_rows(out)                                   # warm-up
+        del full
+        barrier()
+        g0, g1 = (torch.cuda.Event(enable_timing=True),
+                  torch.cuda.Event(enable_timing=True))
+        g0.record()
+        for _ in range(3):
+            full, _ = gather_rows(out)
+            del full
+        g1.record()
+        barrier()
+        gt = torch.tensor([g0.elapsed_time(g1) / 3], device='cuda',
+                          dtype=torch.float64)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        nbytes = int(out.numel() * 4)
+        gather = {'ms': float(gt[0]), 'bytes_per_rank': nbytes,
+                  'recv_gbs_per_rank': (world - 1) * nbytes / (float(gt[0]) * 1e-3) / 1e9,
+                  'api': 'distributed.gather_rows (row counts + one NCCL '
+                         'all-gather of the [frames, 39] blocks; not part of '
+                         'the timed step)'}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,6 +444,8 @@ def main():
         'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
         'cpu_baseline': cpu,
     }
+    if gather is not None:
+        result['gather'] = gather
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

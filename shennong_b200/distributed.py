@@ -116,6 +116,8 @@ def gather_rows(local, group=None):
     gathered = torch.empty((size * height,) + tuple(local.shape[1:]),
                            dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
+    if int(counts_host.min()) == height:
+        return gathered, counts_host      # equal shards: already contiguous
     blocks = [gathered[r * height:r * height + int(counts_host[r])]
               for r in range(size)]
     return torch.cat(blocks, dim=0), counts_host
