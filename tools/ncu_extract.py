@@ -93,6 +93,9 @@ def main():
     ap.add_argument('--top', type=int, default=30)
     ap.add_argument('--sass', default=None,
                     help='regex on the mangled name (template instances)')
+    ap.add_argument('--column', default=None,
+                    help='also rank the source lines by this source-page '
+                         'column, e.g. "L1 Wavefronts Shared"')
     a = ap.parse_args()
 
     raw = ncu_page(a.report, 'raw')
@@ -134,6 +137,23 @@ def main():
         where = f'{loc[0]}:{loc[1]}' if loc else '?'
         print(f'{100 * inst[loc] / ti:.1f},{100 * samp[loc] / ts:.1f},'
               f'{where},"{line}"')
+    if a.column:
+        ic = cols.index(a.column)
+        extra = collections.Counter()
+        for loc, r in zip(seq, data):
+            try:
+                extra[loc] += int(r[ic])
+            except ValueError:
+                pass
+        te = sum(extra.values())
+        print(f'\n# {a.column}: {te} in total')
+        print('pct,value,file:line,source')
+        for loc, v in sorted(extra.items(), key=lambda kv: -kv[1])[:a.top]:
+            line = ''
+            if loc and loc[0] == os.path.basename(a.source):
+                line = text[loc[1] - 1].strip()[:90]
+            where = f'{loc[0]}:{loc[1]}' if loc else '?'
+            print(f'{100 * v / max(te, 1):.1f},{v},{where},"{line}"')
 
 
 if __name__ == '__main__':
