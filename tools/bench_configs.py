@@ -59,6 +59,17 @@ def main():
             pitch=pitch),
         'mfcc_8k_generic_path': None,
     }
+    # the VTLN trainer's warp grid as ONE fused batch of
+    # warps x utterances virtual utterances over the same PCM (21 warps,
+    # 0.85 .. 1.25, pipeline.extract_features_warp_sweep)
+    grid = np.round(np.arange(0.85, 1.2501, 0.02), 2).astype(np.float32)
+    nsweep = max(1, n // len(grid))
+    sweep_packed = engine.PackedAudio.from_packed(
+        None, np.tile(starts[:nsweep], len(grid)),
+        np.tile(lengths[:nsweep], len(grid)), dev=pcm)
+    sweep_warps = np.repeat(grid, nsweep)
+    cases['vtln_sweep_21warps_mfcc_delta'] = FusedPipeline(
+        MfccProcessor(), delta=DeltaPostProcessor())
     results = {}
     for name, pipe in cases.items():
         if args.only and args.only not in name:
@@ -68,6 +79,9 @@ def main():
         plans = pipe._plans()
 
         def run():
+            if name.startswith('vtln_sweep'):
+                return pipe.run_device(sweep_packed, warps=sweep_warps,
+                                       plans=plans)
             return pipe.run_device(packed, speakers=speakers, plans=plans)
         for _ in range(3):
             out, offs, _, _ = run()
