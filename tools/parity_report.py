@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Parity evidence for profiles/: the CUDA path (through the C ABI) against every
+committed golden vector and against the CPU oracle, as numbers rather than
+pass/fail.
+
+    python tools/parity_report.py > profiles/rNN_parity_report.txt     (needs a B200)
+
+Per case: max|a-b| / max|ref| (the gate of the tests, 1e-4), and the
+element-wise relative error over the elements with |ref| >= 1e-3 max|ref|
+(median / 99th percentile / max).  Frame times are compared bit for bit.
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def stats(out, ref):
+    out = np.asarray(out, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = max(np.abs(ref).max(), 1e-30)
+    err = np.abs(out - ref)
+    big = np.abs(ref) >= 1e-3 * scale
+    rel = err[big] / np.abs(ref[big])
+    return (err.max() / scale, np.median(rel), np.percentile(rel, 99), rel.max())
+
+
+def main():
+    import oracle
+    from conftest import synth_utterance
+    from shennong_b200 import Audio
+    from shennong_b200.processor import (
+        EnergyProcessor, FilterbankProcessor, MfccProcessor, PlpProcessor,
+        SpectrogramProcessor)
+    procs = {'mfcc': MfccProcessor, 'filterbank': FilterbankProcessor,
+             'spectrogram': SpectrogramProcessor, 'plp': PlpProcessor,
+             'energy': EnergyProcessor}
+    print('# case, frames x dims, max|a-b|/max|ref|, elementwise rel err '
+          '(|ref| >= 1e-3 max|ref|): median, p99, max, times bit-equal')
+    worst = 0.0
+
+    def row(name, feats, ref, times=None):
+        nonlocal worst
+        s = stats(feats.data, ref)
+        worst = max(worst, s[0])
+        teq = '' if times is None else str(bool(np.array_equal(feats.times, times)))
+        print(f'{name:34s} {feats.shape[0]:5d} x {feats.shape[1]:<3d} '
+              f'{s[0]:.2e}  {s[1]:.2e} {s[2]:.2e} {s[3]:.2e}  {teq}')
+
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'kaldi_compliance.npz'))
+    manifest = json.loads(bytes(g['manifest']).decode())
+    pcm = g['pcm']
+    print('## tests/golden/kaldi_compliance.npz (torchaudio.compliance.kaldi on test.wav)')
+    for name, entry in manifest.items():
+        if entry['kind'] == 'sliding_window_cmn':
+            continue
+        kw = dict(entry['kwargs'])
+        warp = kw.pop('vtln_warp', None)
+        rate = kw.pop('sample_rate', 16000)
+        proc = procs[entry['kind']](sample_rate=rate, dither=0, **kw)
+        audio = Audio(pcm, rate)
+        feats = proc.process(audio) if warp is None else proc.process(audio, vtln_warp=warp)
+        row(name, feats, g[name])
+    p = np.load(os.path.join(ROOT, 'tests', 'golden', 'plp_reference_shim.npz'))
+    meta = json.loads(str(p['meta']))
+    print('## tests/golden/plp_reference_shim.npz (the reference\'s plp.py / energy.py over the pykaldi shim)')
+    for name, entry in meta.items():
+        kw = dict(entry['kwargs'])
+        proc = procs[entry['kind']](dither=0, **kw)
+        warp = entry.get('vtln_warp', 1.0)
+        audio = Audio(pcm, 16000)
+        feats = proc.process(audio) if warp == 1.0 else proc.process(audio, vtln_warp=warp)
+        row(name, feats, p[name], p[name + '.times'])
+    print('## CPU oracle on a 10 s synthetic utterance (998 frames)')
+    sig = synth_utterance(3, 160000)
+    for kind in ('mfcc', 'filterbank', 'spectrogram', 'plp'):
+        feats = procs[kind](dither=0).process(Audio(sig, 16000))
+        row(f'{kind} (oracle)', feats, oracle.features(kind, sig))
+    print(f'# worst max|a-b|/max|ref| = {worst:.2e} (gate 1e-4)')
+
+
+if __name__ == '__main__':
+    main()
