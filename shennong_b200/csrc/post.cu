@@ -215,8 +215,17 @@ __global__ void __launch_bounds__(256) delta_fixed_kernel(const DeltaArgs a) {
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kFixedTile;
   const int64_t lo = row0 - HALO;
   const int nrows = static_cast<int>(min(static_cast<int64_t>(kFixedTile), a.total_frames - row0));
-  const int64_t u0 = cta_find_utt_row(a.frame_offsets, a.nutts, lo < 0 ? 0 : lo);
-  const int64_t first0 = a.frame_offsets[u0], next0 = a.frame_offsets[u0 + 1];
+  // the utterance of the tile's first row: try the equal-length guess first (one
+  // round trip to L2 instead of the search's three when the corpus is uniform)
+  const int64_t row_s = lo < 0 ? 0 : lo;
+  int64_t u0 = static_cast<int64_t>(static_cast<double>(row_s) * static_cast<double>(a.nutts) /
+                                    static_cast<double>(a.total_frames));
+  u0 = min(max(u0, static_cast<int64_t>(0)), a.nutts - 1);
+  int64_t first0 = a.frame_offsets[u0], next0 = a.frame_offsets[u0 + 1];
+  if (!(first0 <= row_s && row_s < next0)) {              // (uniform over the CTA)
+    u0 = cta_find_utt_row(a.frame_offsets, a.nutts, row_s);
+    first0 = a.frame_offsets[u0]; next0 = a.frame_offsets[u0 + 1];
+  }
   const bool uniform = first0 <= lo && lo + NLOAD <= next0;     // tile + halo inside utterance u0
   const bool do_norm = a.norm != nullptr;
   if (!uniform) {
@@ -237,42 +246,79 @@ __global__ void __launch_bounds__(256) delta_fixed_kernel(const DeltaArgs a) {
     }
     __syncthreads();
   }
-  // ---- stage the normalised rows (flat, coalesced) ----
-  {
-    const int32_t g0 = (uniform && do_norm) ? (a.utt_group ? a.utt_group[u0] : static_cast<int32_t>(u0)) : 0;
-    int i = tid / dim, d = tid - i * dim;
-    const int step_i = 256 / dim, step_d = 256 - step_i * dim;
-    for (int e = tid; e < NLOAD * dim; e += 256) {
-      float x = 0.0f;
-      if (uniform || s_hi[i] >= s_lo[i]) {
-        x = a.in[(lo + i) * a.ld_in + d];
+  // Every thread owns ONE column d for the whole tile: 256 / dim rows per pass,
+  // consecutive threads on consecutive elements of a row (coalesced), the few
+  // threads beyond rows_pp * dim idle.  Nothing per element but the load, the
+  // normalisation and the store: no index arithmetic, and in a uniform tile the
+  // column's (scale, offset) sit in two registers.
+  const int rows_pp = 256 / dim;
+  const int tr = tid / dim, d = tid - tr * dim;
+  const bool active = tr < rows_pp;
+  // ---- stage the normalised rows ----
+  if (active) {
+    const float *src = a.in + (lo + tr) * a.ld_in + d;
+    const int64_t src_step = static_cast<int64_t>(rows_pp) * a.ld_in;
+    float *dst = s_x + tr * dim + d;
+    if (uniform) {
+      float scale = 1.0f, offset = 0.0f;
+      if (do_norm) {
+        const int32_t g0 = a.utt_group ? a.utt_group[u0] : static_cast<int32_t>(u0);
+        const float *n = a.norm + static_cast<int64_t>(g0) * 2 * dim;
+        offset = n[d]; scale = n[dim + d];
+      }
+      // batches of four independent loads: with one load in flight per thread
+      // the kernel was latency bound at a quarter of the DRAM bandwidth
+      int i = tr;
+      for (; i + 3 * rows_pp < NLOAD; i += 4 * rows_pp) {
+        float x0 = src[0], x1 = src[src_step], x2 = src[2 * src_step], x3 = src[3 * src_step];
         if (do_norm) {
           // ApplyCmvn: MulColsVec then AddVecToRows (two roundings)
-          const float *n = a.norm + static_cast<int64_t>(uniform ? g0 : s_group[i]) * 2 * dim;
-          x = __fadd_rn(__fmul_rn(x, n[dim + d]), n[d]);
+          x0 = __fadd_rn(__fmul_rn(x0, scale), offset); x1 = __fadd_rn(__fmul_rn(x1, scale), offset);
+          x2 = __fadd_rn(__fmul_rn(x2, scale), offset); x3 = __fadd_rn(__fmul_rn(x3, scale), offset);
         }
+        dst[0] = x0; dst[rows_pp * dim] = x1; dst[2 * rows_pp * dim] = x2; dst[3 * rows_pp * dim] = x3;
+        src += 4 * src_step;
+        dst += 4 * rows_pp * dim;
       }
-      s_x[e] = x;
-      i += step_i; d += step_d;
-      if (d >= dim) { d -= dim; ++i; }
+      for (; i < NLOAD; i += rows_pp) {
+        float x = *src;
+        if (do_norm) x = __fadd_rn(__fmul_rn(x, scale), offset);
+        *dst = x;
+        src += src_step;
+        dst += rows_pp * dim;
+      }
+    } else {
+      for (int i = tr; i < NLOAD; i += rows_pp) {
+        float x = 0.0f;
+        if (s_hi[i] >= s_lo[i]) {
+          x = *src;
+          if (do_norm) {
+            const float *n = a.norm + static_cast<int64_t>(s_group[i]) * 2 * dim;
+            x = __fadd_rn(__fmul_rn(x, n[dim + d]), n[d]);
+          }
+        }
+        *dst = x;
+        src += src_step;
+        dst += rows_pp * dim;
+      }
     }
   }
   __syncthreads();
   // ---- one thread per (row, d): all orders from one pass over the halo ----
-  {
-    int r = tid / dim, d = tid - r * dim;
-    const int step_r = 256 / dim, step_d = 256 - step_r * dim;
-    for (int e = tid; e < nrows * dim; e += 256) {
+  if (active) {
+    float *o_row = a.out + (row0 + tr) * a.ld_out + d;
+    const int64_t out_step = static_cast<int64_t>(rows_pp) * a.ld_out;
+    const float *col = s_x + tr * dim + d;                // row r of the tile = staged row r + HALO
+    for (int r = tr; r < nrows; r += rows_pp) {
       float x[2 * HALO + 1];
       if (uniform) {
 #pragma unroll
-        for (int j = 0; j <= 2 * HALO; ++j) x[j] = s_x[(r + j) * dim + d];
+        for (int j = 0; j <= 2 * HALO; ++j) x[j] = col[j * dim];
       } else {
         const int i0 = r + HALO, clo = s_lo[i0], chi = s_hi[i0];
 #pragma unroll
         for (int j = 0; j <= 2 * HALO; ++j) x[j] = s_x[min(max(r + j, clo), chi) * dim + d];
       }
-      float *o_row = a.out + (row0 + r) * a.ld_out + d;
       int off = 0;                                  // taps of order o start at sum_{i<o} (2 i WINDOW + 1)
 #pragma unroll
       for (int o = 0; o <= ORDER; ++o) {
@@ -283,8 +329,8 @@ __global__ void __launch_bounds__(256) delta_fixed_kernel(const DeltaArgs a) {
         o_row[o * dim] = acc;
         off += 2 * o * WINDOW + 1;
       }
-      r += step_r; d += step_d;
-      if (d >= dim) { d -= dim; ++r; }
+      o_row += out_step;
+      col += rows_pp * dim;
     }
   }
 }
