@@ -409,6 +409,60 @@ __global__ void __launch_bounds__(256) cmvn_accumulate_kernel(
   }
 }
 
+// dim <= 128: the 256 threads are (256 / dim row slices) x (dim columns), so
+// that (almost) every thread works whatever the dimension, and the rows come
+// in batches of four independent loads (one load in flight per thread left the
+// kernel latency bound).  Same arithmetic per element; the slices are added in
+// a fixed order => bit-reproducible.
+__global__ void __launch_bounds__(256) cmvn_accumulate_cols_kernel(
+    const float *feats, int64_t ld, int dim, const int64_t *frame_offsets, const float *weights,
+    double *utt_stats) {
+  __shared__ double s_sum[256], s_sq[256], s_cnt[256];
+  const int64_t u = blockIdx.x;
+  const int64_t first = frame_offsets[u], last = frame_offsets[u + 1];
+  const int tid = threadIdx.x;
+  const int rows_pp = 256 / dim;
+  const int tr = tid / dim, d = tid - tr * dim;
+  double sum = 0.0, sq = 0.0, cnt = 0.0;
+  if (tr < rows_pp) {
+    const int64_t step = rows_pp;
+    int64_t t = first + tr;
+    const float *src = feats + t * ld + d;
+    const int64_t sstep = step * ld;
+    auto add = [&](float v, float w) {
+      if (weights && w == 0.0f) return;
+      cnt += w;
+      sum += static_cast<double>(__fmul_rn(v, w));
+      sq += static_cast<double>(__fmul_rn(__fmul_rn(v, v), w));
+    };
+    for (; t + 3 * step < last; t += 4 * step) {
+      const float v0 = src[0], v1 = src[sstep], v2 = src[2 * sstep], v3 = src[3 * sstep];
+      float w0 = 1.0f, w1 = 1.0f, w2 = 1.0f, w3 = 1.0f;
+      if (weights) { w0 = weights[t]; w1 = weights[t + step]; w2 = weights[t + 2 * step]; w3 = weights[t + 3 * step]; }
+      add(v0, w0); add(v1, w1); add(v2, w2); add(v3, w3);
+      src += 4 * sstep;
+    }
+    for (; t < last; t += step) {
+      add(*src, weights ? weights[t] : 1.0f);
+      src += sstep;
+    }
+  }
+  s_sum[tid] = sum; s_sq[tid] = sq; s_cnt[tid] = cnt;
+  __syncthreads();
+  if (tid < dim) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < rows_pp; ++k) { a += s_sum[k * dim + tid]; b += s_sq[k * dim + tid]; }
+    double *stats = utt_stats + u * 2 * (dim + 1);
+    stats[tid] = a; stats[(dim + 1) + tid] = b;
+    if (tid == 0) {
+      double c = 0.0;
+      for (int k = 0; k < rows_pp; ++k) c += s_cnt[k * dim];       // column 0 of every slice
+      stats[dim] = c;
+      stats[(dim + 1) + dim] = 0.0;
+    }
+  }
+}
+
 __global__ void cmvn_reduce_groups_kernel(const double *utt_stats, int dim, const int64_t *group_ptr,
                                           const int64_t *group_utts, int64_t ngroups,
                                           double *group_stats) {
@@ -634,8 +688,13 @@ extern "C" int snb_cmvn_accumulate(const float *d_feats, int64_t ld, int32_t dim
   // only writes zero statistics)
   if (!d_utt_stats || !d_frame_offsets || dim <= 0 || ld < dim)
     return set_error(SNB_ERR_VALUE, "bad argument");
-  cmvn_accumulate_kernel<<<static_cast<unsigned>(nutts), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      d_feats, ld, dim, d_frame_offsets, d_weights, d_utt_stats);
+  static const bool old_kernel = getenv("SNB_CMVN_COLS") && atoi(getenv("SNB_CMVN_COLS")) == 0;
+  if (dim <= 128 && !old_kernel)
+    cmvn_accumulate_cols_kernel<<<static_cast<unsigned>(nutts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_feats, ld, dim, d_frame_offsets, d_weights, d_utt_stats);
+  else
+    cmvn_accumulate_kernel<<<static_cast<unsigned>(nutts), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+        d_feats, ld, dim, d_frame_offsets, d_weights, d_utt_stats);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
