@@ -260,15 +260,33 @@ struct ResampleArgs {
 };
 
 __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= a.total_down) return;
-  // utterance of this output sample (info[4u] is non-decreasing)
-  int64_t lo = 0, hi = a.nutts;
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (a.info[4 * mid] <= idx) lo = mid; else hi = mid;
+  const int64_t idx0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
+  const int64_t idx = idx0 + threadIdx.x;
+  // utterance of the CTA's first output sample (info[4u] is non-decreasing):
+  // found ONCE per CTA -- the equal-length guess first, else a binary search
+  // by thread 0 -- instead of 14 dependent loads in every thread; the other
+  // threads walk forward from it (a CTA rarely spans more than two utterances)
+  __shared__ int64_t s_u0;
+  if (threadIdx.x == 0) {
+    int64_t g = static_cast<int64_t>(static_cast<double>(idx0) * static_cast<double>(a.nutts) /
+                                     static_cast<double>(a.total_down));
+    g = min(max(g, static_cast<int64_t>(0)), a.nutts - 1);
+    const bool ok = a.info[4 * g] <= idx0 && (g + 1 >= a.nutts || idx0 < a.info[4 * (g + 1)]);
+    if (!ok) {
+      int64_t lo = 0, hi = a.nutts;
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a.info[4 * mid] <= idx0) lo = mid; else hi = mid;
+      }
+      g = lo;
+    }
+    s_u0 = g;
   }
-  const int64_t u = lo, so = idx - a.info[4 * u];
+  __syncthreads();
+  if (idx >= a.total_down) return;
+  int64_t u = s_u0;
+  while (u + 1 < a.nutts && a.info[4 * (u + 1)] <= idx) ++u;
+  const int64_t so = idx - a.info[4 * u];
   const int64_t in0 = a.sample_begin[u], n_in = a.sample_len[u];
   const int64_t unit = so / a.out_unit;
   const int32_t wrapped = static_cast<int32_t>(so - unit * a.out_unit);
