@@ -275,10 +275,23 @@ def extract_features(configuration, utterances, warps=None, njobs=1,
     # one fused batch per sample rate (plans depend on it)
     out = {}
     rates = sorted(set(a.sample_rate for a in audios))
+    groups = []
     for rate in rates:
         idx = [i for i, a in enumerate(audios) if a.sample_rate == rate]
-        out.update(_extract_group(
-            manager, [utts[i] for i in idx], [audios[i] for i in idx], log))
+        groups.append(([utts[i] for i in idx], [audios[i] for i in idx]))
+    by_speaker = 'cmvn' in config and config['cmvn']['by_speaker']
+    spans = len(groups) > 1 and by_speaker and any(
+        len({g for g, (gu, _) in enumerate(groups)
+             if any(u.speaker == spk for u in gu)}) > 1
+        for spk in {u.speaker for u in utts})
+    if spans:
+        # a speaker has utterances at several sample rates: its CMVN statistics
+        # are pooled over all of them (pipeline.py:541-557 accumulates per
+        # speaker whatever the rate; test/test_pipeline.py:347-420)
+        out = _extract_groups_pooled_speakers(manager, groups, log)
+    else:
+        for gutts, gaudios in groups:
+            out.update(_extract_group(manager, gutts, gaudios, log))
     return FeaturesCollection((u.name, out[u.name]) for u in utts)
 
 
@@ -426,6 +439,14 @@ def _extract_group(manager, utts, audios, log):
             pitch_blocks = _separate_pitch(pitch, audios)
 
     names = getattr(pipe, '_group_names', None)
+    return _assemble(manager, proc, delta, pitch, cmvn_mode, utts, audios,
+                     warps, data, offs, stats, names, pitch_blocks, log)
+
+
+def _assemble(manager, proc, delta, pitch, cmvn_mode, utts, audios, warps,
+              data, offs, stats, names, pitch_blocks, log):
+    """Wraps the rows of a group in Features with the reference's properties
+    layout (pipeline.py:570-648)"""
     result = {}
     for i, (utt, audio) in enumerate(zip(utts, audios)):
         block = data[offs[i]:offs[i + 1]]
@@ -474,6 +495,66 @@ def _extract_group(manager, utts, audios, log):
                                           log=log)
         result[utt.name] = feats
     return result
+
+
+def _extract_groups_pooled_speakers(manager, groups, log):
+    """`_extract_group` for several sample-rate groups that share speakers:
+    base features and per-utterance statistics of every group first (kept on
+    the device: with dither a recomputation would not see the same noise),
+    statistics pooled per speaker on the host, then normalisation + deltas
+    per group.  Pitch is pasted on the host."""
+    torch = engine.require_cuda()
+    config = manager.config
+    delta = manager.get_delta_processor() if 'delta' in config else None
+    with_vad = config['cmvn']['with_vad']
+    staged, pooled = [], {}
+    for utts, audios in groups:
+        for audio in audios:
+            if audio.nchannels != 1:
+                raise ValueError(
+                    'signal must have one dimension, but it has {}'.format(
+                        audio.nchannels))
+        proc = manager.get_features_processor(utts[0])
+        has_warp = bool(manager.warps) and proc.name != 'spectrogram'
+        warps = [manager.get_warp(u) for u in utts] if has_warp else None
+        pipe = FusedPipeline(proc, delta=delta, cmvn=None)
+        plans = pipe._plans()
+        packed = engine.PackedAudio([a.astype(np.int16).data for a in audios])
+        batch = engine.Batch(plans['feat'], packed, warps)
+        layout = engine.RowLayout(batch=batch)
+        seed = engine.next_seed() if proc.dither != 0 else 0
+        base = engine.compute_features(plans['feat'], batch, seed=seed)
+        weights = None
+        if with_vad:
+            vad = manager.get_vad_processor()
+            energy = manager.get_energy_processor(utts[0])
+            weights = engine.from_host(np.concatenate([
+                vad.process(energy.process(a)).data.reshape(-1)
+                for a in audios]).astype(np.float32), np.float32)
+        stats = engine.to_host(engine.cmvn_accumulate(base, layout, weights))
+        for utt, st in zip(utts, stats):
+            pooled[utt.speaker] = pooled.get(utt.speaker, 0) + st
+        staged.append((utts, audios, proc, warps, batch, layout, base))
+    out = {}
+    for utts, audios, proc, warps, batch, layout, base in staged:
+        names = sorted({u.speaker for u in utts})
+        stats = np.stack([pooled[n] for n in names])
+        group = np.array([names.index(u.speaker) for u in utts], np.int32)
+        norm = engine.cmvn_norm(engine.from_host(stats, np.float64), True, False)
+        data = engine.to_host(engine.deltas(
+            base, layout, delta.order if delta is not None else 0,
+            delta.window if delta is not None else 1, norm=norm,
+            utt_group=torch.from_numpy(group).to('cuda')))
+        pitch, pitch_blocks = None, None
+        if 'pitch' in config:
+            pitch = (manager.get_pitch_processor(utts[0]),
+                     manager.get_pitch_post_processor())
+            pitch[1]._validate(2)
+            pitch_blocks = _separate_pitch(pitch, audios)
+        out.update(_assemble(
+            manager, proc, delta, pitch, 'speaker', utts, audios, warps, data,
+            batch.frame_offsets, stats, names, pitch_blocks, log))
+    return out
 
 
 def _separate_pitch(pitch, audios):

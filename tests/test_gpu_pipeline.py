@@ -5,6 +5,7 @@ produces the same properties layout (test/test_pipeline.py:276-420)."""
 import numpy as np
 import pytest
 import scipy.io.wavfile
+import scipy.signal
 
 import oracle
 from conftest import scale_close, synth_utterance
@@ -197,3 +198,58 @@ def test_extract_features_warp_and_sweep(corpus):
         pipeline.extract_features_warp(
             no_dither(pipeline.get_default_config(
                 'spectrogram', with_cmvn=False)), utts, 1.1)
+
+
+def test_extract_features_full_mixed_rates(pcm, tmp_path):
+    """The reference's "difficult case" (test/test_pipeline.py:347-420):
+    different sampling rates, float32 audio, segments, and a speaker whose
+    utterances have different rates -- its CMVN statistics are pooled"""
+    import warnings
+    from shennong_b200 import FeaturesCollection
+    wav = str(tmp_path / 'test.wav')
+    wav_f32 = str(tmp_path / 'test.float32.wav')
+    wav_8k = str(tmp_path / 'test.8k.wav')
+    scipy.io.wavfile.write(wav, 16000, pcm)
+    scipy.io.wavfile.write(wav_f32, 16000, (pcm / 32768.0).astype(np.float32))
+    scipy.io.wavfile.write(
+        wav_8k, 8000, np.round(scipy.signal.resample_poly(
+            pcm.astype(np.float64), 1, 2)).astype(np.int16))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')        # u3 is longer than its file
+        index = Utterances([
+            ('u1', wav, 's1', 0, 1),
+            ('u2', wav_f32, 's2', 1, 1.2),
+            ('u3', wav_8k, 's1', 1, 3)])
+    config = pipeline.get_default_config(
+        'mfcc', with_cmvn=True, with_delta=True, with_pitch='kaldi')
+    config['cmvn']['with_vad'] = False
+    feats = pipeline.extract_features(config, index, njobs=2)
+    for utt in ('u1', 'u2', 'u3'):
+        assert feats[utt].dtype == np.float32
+    p1, p2, p3 = (feats[u].properties for u in ('u1', 'u2', 'u3'))
+    assert p1['audio']['duration'] == 1.0
+    assert p2['audio']['duration'] == pytest.approx(0.2)
+    assert p3['audio']['duration'] < 0.5
+    assert p1['mfcc'] == p2['mfcc']
+    assert p1['mfcc']['sample_rate'] != p3['mfcc']['sample_rate']
+    assert p1.keys() == {
+        'audio', 'mfcc', 'cmvn', 'pitch', 'delta', 'speaker', 'pipeline'}
+    assert p1.keys() == p2.keys() == p3.keys()
+    assert p1['pipeline'] == p2['pipeline'] == p3['pipeline']
+    assert feats['u1'].shape == (98, 42)
+    assert feats['u2'].shape == (18, 42)
+    assert feats['u3'].shape == (40, 42)
+    assert feats['u2'].data[:, :13].mean() == pytest.approx(0.0, abs=1e-5)
+    assert feats['u2'].data[:, :13].std() == pytest.approx(1.0, abs=1e-5)
+    data = np.vstack((feats['u1'].data[:, :13], feats['u3'].data[:, :13]))
+    assert data.mean() == pytest.approx(0.0, abs=1e-5)
+    assert data.std() == pytest.approx(1.0, abs=1e-5)
+    assert np.abs(data.mean()) <= np.abs(feats['u1'].data[:, :13].mean())
+    assert np.abs(data.std() - 1.0) <= np.abs(
+        feats['u1'].data[:, :13].std() - 1.0)
+    assert np.abs(data.mean()) <= np.abs(feats['u3'].data[:, :13].mean())
+    assert np.abs(data.std() - 1.0) <= np.abs(
+        feats['u3'].data[:, :13].std() - 1.0)
+    filename = str(tmp_path / 'feats.npz')
+    feats.save(filename)
+    assert FeaturesCollection.load(filename) == feats
