@@ -16,7 +16,35 @@ __all__ = ['Audio', 'Features', 'FeaturesCollection', 'Utterance',
            'Utterances']
 
 
-def version(type=str):
-    """Version of the engine as a string or a tuple of integers"""
-    numbers = (0, 1, 0)
-    return '.'.join(str(n) for n in numbers) if type is str else numbers
+__version__ = '0.1.0'
+
+
+def url():
+    """Where the documentation of the reference API lives (the engine keeps it)"""
+    return 'https://docs.cognitive-ml.fr/shennong'
+
+
+def version(type=str, full=False):
+    """Version of the engine as a string or a tuple of strings
+
+    Same call surface as ``shennong.version`` (shennong/__init__.py:41-64):
+    `type` is ``str``/``tuple`` (or their names), `full` keeps any
+    pre-release field after (major, minor, patch).
+    """
+    if type not in (str, tuple, 'str', 'tuple'):
+        raise ValueError(
+            'version type must be str or tuple, it is {}'.format(type))
+    fields = tuple(__version__.split('.'))
+    if not full:
+        fields = fields[:3]
+    return fields if type in (tuple, 'tuple') else '.'.join(fields)
+
+
+def version_long():
+    """Version, origin and licence note in a few lines"""
+    import datetime
+    return (
+        'shennong_b200-{} (B200-native engine for the shennong feature path)\n'
+        'API modelled on shennong (copyright 2018-{} Inria, licence GPL3)\n'
+        'see the documentation of that API at {}\n'.format(
+            version(), datetime.date.today().year, url()))

@@ -115,7 +115,7 @@ class BaseProcessor:
                 continue
             if param.kind == param.VAR_POSITIONAL:
                 raise RuntimeError(
-                    f'processors must declare their parameters in the '
+                    f'processors must specify their parameters in the '
                     f'signature of __init__ (no varargs): {cls}')
             names.append(param.name)
         return sorted(names)

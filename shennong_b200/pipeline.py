@@ -295,6 +295,20 @@ def extract_features(configuration, utterances, warps=None, njobs=1,
     return FeaturesCollection((u.name, out[u.name]) for u in utts)
 
 
+def _check_environment(njobs, log=get_logger('pipeline', 'warning')):
+    """Warns when several host jobs meet implicit (OpenMP/BLAS) threading
+    (shennong/pipeline.py:299-312); here `njobs` only loads audio files, the
+    warning is kept for scripts that rely on it"""
+    if njobs == 1:
+        return
+    nthreads = os.environ.get('OMP_NUM_THREADS')
+    if nthreads is None or not nthreads.isdigit() or int(nthreads) != 1:
+        log.warning(
+            'working on %s threads but implicit parallelism is active, '
+            'this may slow down the processing. Set the environment variable '
+            'OMP_NUM_THREADS=1 to disable this warning', njobs)
+
+
 def _warp_setup(configuration, utterances, njobs, log):
     """Shared front end of the warp extractions: (manager, utts, audios)"""
     njobs = get_njobs(njobs, log=log)

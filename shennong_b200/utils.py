@@ -71,3 +71,25 @@ def list_files_with_extension(directory, extension, abspath=False,
     if not (abspath or realpath):
         found = [os.path.relpath(f, directory) for f in found]
     return sorted(found)
+
+
+class CatchExceptions:
+    """Decorator for command-line entry points: runs the function and turns
+    the usual failures into a one-line message on stderr and exit code 1
+    (same surface as shennong/utils.py:147-190)"""
+    def __init__(self, function):
+        self.function = function
+
+    def __call__(self):
+        try:
+            self.function()
+        except KeyboardInterrupt:
+            self.exit('keyboard interruption, exiting')
+        except (OSError, ValueError, RuntimeError, AssertionError) as err:
+            self.exit('fatal error: {}'.format(err))
+
+    @staticmethod
+    def exit(message):
+        import sys
+        sys.stderr.write(message.strip() + '\n')
+        sys.exit(1)

@@ -21,7 +21,7 @@ VALID_FORMATS = {
 def _as_float(value, what):
     try:
         return float(value)
-    except ValueError:
+    except (TypeError, ValueError):
         raise ValueError(f'cannot cast {what} as float: {value}') from None
 
 
@@ -35,6 +35,11 @@ class Utterance:
         self._speaker = args[2] if len(args) in (3, 5) else None
         self._tstart = self._tstop = None
         if len(args) >= 4:
+            if (args[-2] is None) != (args[-1] is None):
+                raise ValueError(
+                    'both tstart and tstop must be defined or None, but '
+                    f'(tstart, tstop)=({args[-2]}, {args[-1]})')
+        if len(args) >= 4 and args[-1] is not None:
             self._tstart = _as_float(args[-2], 'tstart')
             self._tstop = _as_float(args[-1], 'tstop')
             if self._tstart < 0 or self._tstart >= self._tstop:
