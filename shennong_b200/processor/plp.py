@@ -15,6 +15,60 @@ from shennong_b200.features import Features
 from shennong_b200.processor.base import MelFeaturesProcessor
 
 
+class RastaFilter:
+    """RASTA band-pass filter applied frame by frame (host side)
+
+    Public helper of the reference (plp.py:64-146, after rastamat / rasta_py):
+    a 5-tap FIR differentiator followed by a single pole at 0.94, run on the
+    (log) mel energies along time.  The first four frames only prime the
+    filter memory and yield zeros (ones after the inverse log).  The product
+    path runs the same recursion on the device (``rasta_kernel``); this class
+    keeps the reference's Python entry point for scripts that filter frames
+    themselves.
+
+    Parameters
+    ----------
+    size : int
+        Dimension of the frames to filter
+    """
+    def __init__(self, size):
+        import scipy.signal
+        self._lfilter, self._lfilter_zi = scipy.signal.lfilter, scipy.signal.lfilter_zi
+        taps = np.arange(-2, 3)
+        self._num = -taps / np.sum(taps ** 2)
+        self._den = np.array([1, -0.94])
+        self._size = size
+        self.reset()
+
+    def reset(self):
+        """Forgets the past frames"""
+        self._seen = 0
+        self._head = []
+        zi = self._lfilter_zi(self._num, 1)
+        self._memory = zi if self._size == 1 else np.repeat(
+            zi[:, None], self._size, axis=1)
+
+    def filter(self, frame, do_log=True):
+        """Filters one frame (shape [size]); `do_log` moves to the log domain
+        first and back afterwards, else `frame` is taken as log energies"""
+        x = frame
+        if do_log:
+            x = np.log(x + np.finfo(x.dtype).eps)
+        if self._seen < 4:
+            self._head.append(x)
+            y = np.zeros(x.shape)
+            if self._seen == 3:
+                head = np.asarray(self._head)
+                _, self._memory = self._lfilter(
+                    self._num, 1, head, zi=self._memory * head[0], axis=0)
+        else:
+            y, self._memory = self._lfilter(
+                self._num, self._den, [x], zi=self._memory, axis=0)
+        self._seen += 1
+        y = np.atleast_2d(y)[0, :].astype(x.dtype)
+        return np.exp(y) if do_log else y
+
+
 def _check_num_ceps(proc, value):
     value = int(value)
     if value <= 0:

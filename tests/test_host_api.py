@@ -276,3 +276,28 @@ def test_param_types_and_validation():
     props = MfccProcessor().get_properties(vtln_warp=1.0)
     assert props['pipeline'] == [{'name': 'mfcc', 'columns': [0, 12]}]
     assert props['mfcc']['vtln_warp'] == 1.0
+
+
+def test_rasta_filter_frame_by_frame_equals_whole_signal():
+    """RastaFilter (public helper of plp.py) against the whole-signal form of
+    the same filter (rasta_py), as test/processor/test_plp.py:94-124 does"""
+    import scipy.signal
+    from shennong_b200.processor.plp import RastaFilter
+    taps = -np.arange(-2, 3) / 10.0
+    rng = np.random.default_rng(3)
+    n = 795
+    data = np.stack([np.sin(2 * np.pi * np.arange(n) * 200 / 16000),
+                     rng.random(n), np.eye(1, n)[0]], axis=1)
+    rasta = RastaFilter(3)
+    framewise = np.array([rasta.filter(row, do_log=False) for row in data])
+    whole = np.zeros_like(data)
+    for c in range(3):
+        col = data[:, c]
+        zi = scipy.signal.lfilter_zi(taps, 1)
+        _, zi = scipy.signal.lfilter(taps, 1, col[:4], zi=zi * col[0])
+        whole[4:, c], _ = scipy.signal.lfilter(taps, [1, -0.94], col[4:], zi=zi)
+    assert np.array_equal(framewise, whole)
+    # log domain round trip: the four priming frames come out as exp(0)
+    rasta.reset()
+    out = np.array([rasta.filter(row + 1.0) for row in data])
+    assert np.all(out[:4] == 1.0) and np.isfinite(out).all()
