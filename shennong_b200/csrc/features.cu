@@ -753,7 +753,18 @@ struct GenArgs {
   uint64_t seed;
 };
 
-__device__ __forceinline__ int64_t find_utt(const int64_t *offsets, int64_t nutts, int64_t row) {
+// (total = offsets[nutts]: the equal-length guess is tried first -- two loads
+// instead of a chain of ~log2(nutts) dependent ones per frame)
+__device__ __forceinline__ int64_t find_utt(const int64_t *offsets, int64_t nutts, int64_t row, int64_t total) {
+#ifndef SNB_UTT_GUESS
+#define SNB_UTT_GUESS 1
+#endif
+  if (SNB_UTT_GUESS && total > 0) {
+    int64_t g = static_cast<int64_t>(static_cast<double>(row) * static_cast<double>(nutts) /
+                                     static_cast<double>(total));
+    g = min(max(g, static_cast<int64_t>(0)), nutts - 1);
+    if (offsets[g] <= row && row < offsets[g + 1]) return g;
+  }
   int64_t lo = 0, hi = nutts;      // offsets[lo] <= row < offsets[hi]
   while (hi - lo > 1) {
     const int64_t mid = (lo + hi) >> 1;
@@ -790,7 +801,7 @@ generic_features_kernel(const GenArgs a) {
 
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kGenWarps + warp; row < a.total_frames;
        row += static_cast<int64_t>(gridDim.x) * kGenWarps) {
-    const int64_t utt = find_utt(a.frame_offsets, a.nutts, row);
+    const int64_t utt = find_utt(a.frame_offsets, a.nutts, row, a.total_frames);
     const int64_t f = row - a.frame_offsets[utt];
     const int64_t utt_off = a.sample_begin[utt];
     const int64_t n = a.sample_len[utt];
@@ -965,7 +976,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) plp_from_mel_kernel(const PlpM
   tt.dct_stride = 0;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kGenWarps + warp; row < a.total_frames;
        row += static_cast<int64_t>(gridDim.x) * kGenWarps) {
-    const int64_t utt = find_utt(a.frame_offsets, a.nutts, row);
+    const int64_t utt = find_utt(a.frame_offsets, a.nutts, row, a.total_frames);
     // all the utterances of a RASTA batch share the blob unless VTLN warps differ
     int mel_idx = 0;
     if (a.utt_mel_idx) mel_idx = a.utt_mel_idx[utt];

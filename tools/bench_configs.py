@@ -57,7 +57,8 @@ def main():
             FilterbankProcessor(), delta=DeltaPostProcessor(),
             cmvn='speaker', vad=VadPostProcessor(), energy=EnergyProcessor(),
             pitch=pitch),
-        'mfcc_8k_generic_path': None,
+        # generic kernel (any FFT size): the same PCM read as 8 kHz audio, N = 256
+        'mfcc_8k_generic_path': FusedPipeline(MfccProcessor(sample_rate=8000)),
     }
     # the VTLN trainer's warp grid as ONE fused batch of
     # warps x utterances virtual utterances over the same PCM (21 warps,
