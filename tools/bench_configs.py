@@ -71,6 +71,13 @@ def main():
     sweep_warps = np.repeat(grid, nsweep)
     cases['vtln_sweep_21warps_mfcc_delta'] = FusedPipeline(
         MfccProcessor(), delta=DeltaPostProcessor())
+    # ragged batch (load balance): the same buffer read as utterances of 2..10 s
+    ragged_lengths = np.random.default_rng(7).integers(
+        32000, bench.UTT_SAMPLES + 1, size=n).astype(np.int64)
+    ragged_packed = engine.PackedAudio.from_packed(
+        None, starts, ragged_lengths, dev=pcm)
+    cases['cfg3_ragged_2_10s_mfcc_delta_cmvn'] = FusedPipeline(
+        MfccProcessor(), delta=DeltaPostProcessor(), cmvn='utterance')
     results = {}
     for name, pipe in cases.items():
         if args.only and args.only not in name:
@@ -82,6 +89,9 @@ def main():
         def run():
             if name.startswith('vtln_sweep'):
                 return pipe.run_device(sweep_packed, warps=sweep_warps,
+                                       plans=plans)
+            if 'ragged' in name:
+                return pipe.run_device(ragged_packed, speakers=speakers,
                                        plans=plans)
             return pipe.run_device(packed, speakers=speakers, plans=plans)
         for _ in range(3):
