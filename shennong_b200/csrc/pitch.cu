@@ -597,7 +597,13 @@ __global__ void __launch_bounds__(kPitchThreads, SNB_PITCH_MINB) pitch_track_ker
 // brute-force reference step (oracle/kaldi_oracle.c, orc_compute_pitch).
 // ---------------------------------------------------------------------------
 constexpr int kTrackWarpsMax = 20;   // (24 fit in shared memory but run erratically slower)
-constexpr int kA1Log2 = 6, kA1 = 1 << kA1Log2;
+#ifndef SNB_PITCH_A1LOG2
+#define SNB_PITCH_A1LOG2 6
+#endif
+#ifndef SNB_PITCH_TMAX
+#define SNB_PITCH_TMAX 32
+#endif
+constexpr int kA1Log2 = SNB_PITCH_A1LOG2, kA1 = 1 << kA1Log2;
 
 struct WarpSmem {           // per-warp float offsets
   int win, pre, np, nv, prev, cost, abp, total;
@@ -854,7 +860,7 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
       for (int ls = kA1Log2 - 1; ls >= 0; --ls) {
         const int s = 1 << ls;
         const int nodd = (ns - 2 >= s) ? ((ns - 2 - s) >> (ls + 1)) + 1 : 0;
-        const int T = min(32, 2 * s + 2);
+        const int T = min(SNB_PITCH_TMAX, 2 * s + 2);
 #pragma unroll 1
         for (int k0 = 0; k0 < nodd; k0 += 32) {
           const int k = k0 + lane;
