@@ -301,3 +301,51 @@ def test_rasta_filter_frame_by_frame_equals_whole_signal():
     rasta.reset()
     out = np.array([rasta.filter(row + 1.0) for row in data])
     assert np.all(out[:4] == 1.0) and np.isfinite(out).all()
+
+
+def test_package_helpers_and_placeholders(capsys, tmp_path, pcm):
+    """Small API surface the reference's own tests exercise (test_base.py,
+    test_utils.py, test_utterances.py, test_pipeline.py:215-220)"""
+    import os
+    import scipy.io.wavfile
+    import shennong_b200
+    from shennong_b200 import Utterance, logger, pipeline, utils
+    assert '.'.join(shennong_b200.version(type=tuple)) == shennong_b200.version()
+    assert len(shennong_b200.version(type='tuple', full=False)) <= len(
+        shennong_b200.version(type=tuple, full=True))
+    with pytest.raises(ValueError, match='version type must be str or tuple'):
+        shennong_b200.version(type=int)
+    assert shennong_b200.version() in shennong_b200.version_long()
+    assert 'shennong' in shennong_b200.url()
+
+    @utils.CatchExceptions
+    def fails():
+        raise ValueError('foo')
+    with pytest.raises(SystemExit):
+        fails()
+    assert 'fatal error: foo' in capsys.readouterr().err
+
+    @utils.CatchExceptions
+    def interrupted():
+        raise KeyboardInterrupt
+    with pytest.raises(SystemExit):
+        interrupted()
+    assert 'keyboard interruption' in capsys.readouterr().err
+
+    wav = str(tmp_path / 'a.wav')
+    scipy.io.wavfile.write(wav, 16000, pcm)
+    for args in ((0, wav, None, 1), (0, wav, 0, None)):
+        with pytest.raises(ValueError, match='both tstart and tstop'):
+            Utterance(*args)
+    with pytest.raises(ValueError, match='cannot cast tstart as float'):
+        Utterance(0, wav, 'abc', 0)
+
+    os.environ.pop('OMP_NUM_THREADS', None)
+    pipeline._check_environment(2, log=logger.get_logger('test', 'info'))
+    assert ('working on 2 threads but implicit parallelism is active'
+            in capsys.readouterr().err)
+
+    from shennong_b200.processor import BottleneckProcessor, VtlnProcessor
+    for cls in (BottleneckProcessor, VtlnProcessor):
+        with pytest.raises(NotImplementedError, match='not part of'):
+            cls()
