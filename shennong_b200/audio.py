@@ -125,6 +125,13 @@ class Audio:
         filename = str(filename)
         if os.path.isfile(filename):
             raise ValueError(f'{filename}: file already exists')
+        if '.' not in os.path.basename(filename):
+            raise ValueError(
+                f'{filename}: cannot write audio file without extension')
+        if filename.split('.')[-1].lower() != 'wav':
+            raise ValueError(
+                f'{filename}: cannot write file, only the wav format is '
+                'supported (flac/mp3 need ffmpeg, out of scope)')
         try:
             scipy.io.wavfile.write(filename, self.sample_rate, self.data)
         except Exception as err:
@@ -141,13 +148,27 @@ class Audio:
             return self
         return Audio(self.data[:, index], self.sample_rate, validate=False)
 
-    def resample(self, sample_rate):
-        """Resampled signal (FFT method of scipy.signal, the reference's
-        'scipy' backend, shennong/audio.py:412-423)"""
+    def resample(self, sample_rate, backend='sox'):
+        """Resampled signal
+
+        Same call surface as the reference (shennong/audio.py:358-423):
+        `backend` is 'sox' or 'scipy'.  The sox binary is not available to this
+        engine, so both names run the FFT method of scipy.signal -- what the
+        reference itself falls back to without sox.
+        """
+        if backend not in ('sox', 'scipy'):
+            raise ValueError(f'backend must be sox or scipy, it is {backend}')
         if sample_rate == self.sample_rate:
             return self
-        nsamples = int(self.nsamples * sample_rate / self.sample_rate)
-        data = scipy.signal.resample(self.data, nsamples)
+        try:
+            nsamples = int(self.nsamples * sample_rate / self.sample_rate)
+            if sample_rate <= 0 or nsamples <= 0:
+                raise ValueError('no sample left')
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore', category=FutureWarning)
+                data = scipy.signal.resample(self.data, nsamples)
+        except (ValueError, ZeroDivisionError):
+            raise ValueError(f'resampling at {sample_rate} failed!') from None
         return Audio(data.astype(self.dtype), sample_rate, validate=False)
 
     @staticmethod
