@@ -349,3 +349,41 @@ def test_package_helpers_and_placeholders(capsys, tmp_path, pcm):
     for cls in (BottleneckProcessor, VtlnProcessor):
         with pytest.raises(NotImplementedError, match='not part of'):
             cls()
+
+
+def test_compat_alias_runs_shennong_imports():
+    """shennong_b200.compat: code written against `shennong` imports resolves
+    to the engine; out-of-scope modules are stubs that fail when used"""
+    import subprocess
+    import sys
+    code = '''
+import shennong_b200.compat as compat
+assert compat.install()
+import shennong, shennong_b200
+assert shennong is shennong_b200
+from shennong.processor.mfcc import MfccProcessor
+from shennong.postprocessor.cmvn import CmvnPostProcessor
+from shennong import pipeline, Features, Audio
+import shennong_b200.processor.mfcc as real
+assert MfccProcessor is real.MfccProcessor
+assert 'mfcc' in pipeline.valid_features()
+from shennong.alignment import AlignmentCollection
+try:
+    AlignmentCollection.load('x')
+except NotImplementedError:
+    pass
+else:
+    raise SystemExit('stub did not raise')
+compat.uninstall()
+import importlib
+try:
+    importlib.import_module('shennong.audio')
+except ModuleNotFoundError:
+    print('ok')
+'''
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True,
+                         text=True, cwd=root, timeout=300)
+    assert res.returncode == 0 and res.stdout.strip() == 'ok', (
+        res.stdout + res.stderr)
