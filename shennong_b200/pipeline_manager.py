@@ -154,7 +154,7 @@ class PipelineManager:
         proc.sample_rate = self._sample_rate(utterance)
         return self._configure(proc)
 
-    def get_vad_processor(self, utterance=None):
+    def get_vad_processor(self, _=None):
         return self._configure(
             self.get_processor_class('vad')(**self.config['cmvn']['vad']))
 
@@ -172,11 +172,11 @@ class PipelineManager:
         return self._configure(
             self.get_processor_class('kaldi_pitch')(**params))
 
-    def get_pitch_post_processor(self, utterance=None):
+    def get_pitch_post_processor(self, _=None):
         return self._configure(self.get_processor_class('kaldi_pitch_post')(
             **self.config['pitch']['postprocessing']))
 
-    def get_delta_processor(self, utterance=None):
+    def get_delta_processor(self, _=None):
         return self._configure(
             self.get_processor_class('delta')(**self.config['delta']))
 
