@@ -28,22 +28,20 @@ def get_njobs(njobs=None, log=null_logger()):
     return njobs
 
 
-def array2list(obj):
-    """Recursively converts numpy arrays of `obj` to lists"""
-    if isinstance(obj, dict):
-        return {k: array2list(v) for k, v in obj.items()}
-    if isinstance(obj, np.ndarray):
-        return obj.tolist()
-    return obj
+def array2list(seq):
+    """`seq` with every numpy array (also inside nested dicts) turned into a list"""
+    if isinstance(seq, np.ndarray):
+        return seq.tolist()
+    if isinstance(seq, dict):
+        return {key: array2list(value) for key, value in seq.items()}
+    return seq
 
 
-def list2array(obj):
-    """Recursively converts lists of `obj` to numpy arrays"""
-    if isinstance(obj, list):
-        return np.asarray(obj)
-    if isinstance(obj, dict):
-        return {k: list2array(v) for k, v in obj.items()}
-    return obj
+def list2array(seq):
+    """Inverse of :func:`array2list`: lists (also inside nested dicts) become arrays"""
+    if isinstance(seq, dict):
+        return {key: list2array(value) for key, value in seq.items()}
+    return np.asarray(seq) if isinstance(seq, list) else seq
 
 
 def dict_equal(dict1, dict2):

@@ -39,6 +39,10 @@ CLASSES = {
 }
 
 
+FUNCTION_MODULES = ['shennong/pipeline.py', 'shennong/utils.py', 'shennong/serializers.py',
+                    'shennong/window.py', 'shennong/logger.py', 'shennong/__init__.py']
+
+
 def ref_signature(fn):
     names = [a.arg for a in fn.args.args][1:]
     defaults = []
@@ -113,6 +117,38 @@ def main():
                         continue         # an argument the engine does not need
                     if not same_default(rd, od):
                         problems.append(f'{node.name}.{item.name}: default of {n}: {rd!r} vs {od!r}')
+    nfuncs = 0
+    for path in FUNCTION_MODULES:
+        tree = ast.parse(open(os.path.join(ref_root, path)).read())
+        name = path[:-3].replace('/', '.').replace('.__init__', '')
+        mod = importlib.import_module(name)
+        for item in tree.body:
+            if not isinstance(item, ast.FunctionDef) or item.name.startswith('_'):
+                continue
+            nfuncs += 1
+            fn = getattr(mod, item.name, None)
+            if fn is None:
+                problems.append(f'{name}.{item.name}: function missing')
+                continue
+            ours = [(n, p.default if p.default is not inspect.Parameter.empty else '<required>')
+                    for n, p in inspect.signature(fn).parameters.items()
+                    if p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL)]
+            names = [a.arg for a in item.args.args]
+            defaults = []
+            for d in item.args.defaults:
+                try:
+                    defaults.append(ast.literal_eval(d))
+                except ValueError:
+                    defaults.append(ast.unparse(d))
+            first = len(names) - len(defaults)
+            ref = [(n, defaults[i - first] if i >= first else '<required>') for i, n in enumerate(names)]
+            if [n for n, _ in ref] != [n for n, _ in ours]:
+                problems.append(f'{name}.{item.name}: arguments {[n for n, _ in ref]} vs {[n for n, _ in ours]}')
+                continue
+            for (n, rd), (_, od) in zip(ref, ours):
+                if not same_default(rd, od) and not (isinstance(rd, str) and rd in ('int', 'str', 'tuple')):
+                    problems.append(f'{name}.{item.name}: default of {n}: {rd!r} vs {od!r}')
+    print(f'# {nfuncs} public module-level functions compared')
     print(f'# {nclasses} classes, {nmethods} public methods / constructors compared '
           f'({ref_root} parsed with ast, shennong_b200 introspected)')
     for p in problems:
