@@ -286,6 +286,10 @@ int snb_convert_f64_to_f32(const double *d_in, float *d_out, int64_t n,
 /* ---- pitch --------------------------------------------------------------- */
 /* frames compute_kaldi_pitch returns for nsamples (pitch_kaldi.py:298) */
 int64_t snb_pitch_num_frames(int64_t nsamples, const snb_pitch_opts *po);
+/* the same for n utterance lengths at once (HOST arrays): a corpus is planned
+ * (row offsets of every utterance) before its first chunk is uploaded */
+void snb_pitch_num_frames_array(const int64_t *nsamples, int64_t n,
+                                const snb_pitch_opts *po, int64_t *out);
 /* bytes of DEVICE scratch snb_compute_pitch needs for this batch */
 int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch);
 /* replaces kaldi.feat.pitch.compute_kaldi_pitch(opts, wave)
@@ -297,11 +301,20 @@ int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch,
                       void *stream);
 int32_t snb_process_pitch_dim(const snb_pitch_post_opts *o);
 /* replaces kaldi.feat.pitch.process_pitch(opts, raw) (pitch_kaldi.py:536-537)
- * for delay == 0; d_out DEVICE float32[total_frames, ld_out];
+ * d_out DEVICE float32[total_frames + nutts * delay, ld_out]: with delay = d
+ * (>= 0; Kaldi asserts on a negative one) an utterance of F > 0 frames gives
+ * F + d rows, row t = features of frame max(0, t - d), written from row
+ * frame_offsets[u] + u * d (d = 0: the input geometry).  With
+ * d_out_frame_offsets (DEVICE int64[nutts+1], may be NULL) the rows of
+ * utterance u go to out_frame_offsets[u] instead and only the first
+ * out_frame_offsets[u+1] - out_frame_offsets[u] of them are written: pasting
+ * pitch next to features that have one or two frames less is the trim of
+ * Features.concatenate(tolerance=2) (features.py:350-437, pipeline.py:639-641);
  * max_frames_per_utt = longest utterance of the batch in frames (launch
  * geometry); seed drives the delta-pitch noise (ignored when its stddev is 0) */
 int snb_process_pitch(const snb_pitch_post_opts *o, const float *d_raw,
                       int64_t ld_raw, const int64_t *d_frame_offsets,
+                      const int64_t *d_out_frame_offsets,
                       int64_t nutts, int64_t total_frames,
                       int64_t max_frames_per_utt, uint64_t seed, float *d_out,
                       int64_t ld_out, void *stream);

@@ -5,17 +5,23 @@
 // pitch-functions.cc + resample.cc in OFFLINE use: one AcceptWaveform() with
 // the resampler unflushed followed by InputFinished().
 //
-//   k1  resample_kernel      16k -> 4k windowed-sinc (LinearResample), one
-//                            thread per output sample, all utterances at once
-//   k2  pitch_track_kernel   one CTA per utterance, sequential over frames:
-//                            NCCF at the integer lags, sinc-upsample to the
-//                            log-spaced lags (ArbitraryResample), one exact
-//                            Viterbi step (min-plus over all states), back-
-//                            pointers to a per-CTA scratch; then backtrace and
-//                            the (NCCF, pitch) rows
-//   k3  process_pitch_kernel POV / normalised log-pitch / delta / raw log-pitch
+//   k1  resample_kernel       16k -> 4k windowed-sinc (LinearResample), one
+//                             thread per output sample, all utterances at once
+//   k2  pitch_ballast_kernel  per-utterance mean square -> NCCF ballast
+//   k3  pitch_nccf_kernel     frame-parallel: NCCF at the integer lags, sinc-
+//                             upsampling to the log-spaced lags (Arbitrary-
+//                             Resample), local cost of every Viterbi state
+//   k4  pitch_viterbi_kernel  warp per utterance, sequential over frames: exact
+//                             monotone Viterbi step, backpointers, backtrace,
+//                             the (NCCF, pitch) rows
+//   k5  process_pitch_kernel  POV / normalised log-pitch / delta / raw log-pitch
+//
+// Every dot product of k1/k3/k4 accumulates in double in index order and is
+// rounded to float once, like the oracle (oracle/kaldi_oracle.c): the Viterbi
+// state sequence is bit-identical to the oracle's (tests/test_gpu_pitch.py).
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 
 #include "device_utils.cuh"
@@ -23,8 +29,6 @@
 
 namespace snb {
 
-constexpr int kPitchThreads = 256;
-constexpr int kMaxStatesPerThread = 8;
 
 struct PitchTables {
   // host copies
@@ -37,10 +41,13 @@ struct PitchTables {
   std::vector<float> lags, pen;                 // [nstates]
   std::vector<int32_t> up_first, up_nw;         // [nstates]
   std::vector<float> up_w;                      // [nstates, up_nw_max]
+  int32_t ns4, ns_pad;                          // nstates rounded up to 4 (cost rows) / 2 (tap rows)
+  std::vector<double> up_w_t;                   // [up_nw_max, ns_pad] same taps, state-contiguous doubles
   // device copies (one allocation)
   void *d_blob = nullptr;
   const int32_t *d_down_first, *d_down_nw, *d_up_first, *d_up_nw;
   const float *d_down_w, *d_lags, *d_pen, *d_up_w;
+  const double *d_up_w_t;
 };
 
 static int32_t gcd_i32(int32_t a, int32_t b) {
@@ -154,7 +161,7 @@ int pitch_plan_init(snb_plan *plan) {
   t->full_len = t->basic_len + t->last_lag;
   if (t->nmeas <= 0 || t->nstates <= 0 || t->shift <= 0 || t->basic_len <= 0)
     return set_error(SNB_ERR_OPTION, "invalid pitch extraction options");
-  if (t->nstates > kPitchThreads * kMaxStatesPerThread || t->full_len > 4096 || t->nmeas > 1024)
+  if (t->nstates > 4096 || t->full_len > 4096 || t->nmeas > 1024)
     return set_error(SNB_ERR_UNSUPPORTED, "pitch options outside the GPU path limits");
   // --- ArbitraryResample (float arithmetic as in resample.cc) ---
   const float up_cutoff = o.resample_freq * 0.5f;
@@ -180,6 +187,12 @@ int pitch_plan_init(snb_plan *plan) {
   t->up_w.assign(static_cast<size_t>(t->nstates) * t->up_nw_max, 0.0f);
   for (int32_t i = 0; i < t->nstates; ++i)
     std::copy(uw[i].begin(), uw[i].end(), t->up_w.begin() + static_cast<size_t>(i) * t->up_nw_max);
+  t->ns4 = (t->nstates + 3) & ~3;
+  t->ns_pad = (t->nstates + 1) & ~1;
+  t->up_w_t.assign(static_cast<size_t>(t->up_nw_max) * t->ns_pad, 0.0);
+  for (int32_t i = 0; i < t->nstates; ++i)
+    for (int32_t j = 0; j < t->up_nw[i]; ++j)
+      t->up_w_t[static_cast<size_t>(j) * t->ns_pad + i] = static_cast<double>(uw[i][j]);
   // --- Viterbi transition penalties: (i-j)^2 * inter_frame_factor ---
   const float delta_pitch_sq = static_cast<float>(std::pow(std::log(1.0 + static_cast<double>(o.delta_pitch)), 2.0));
   const float factor = delta_pitch_sq * o.penalty_factor;
@@ -198,6 +211,9 @@ int pitch_plan_init(snb_plan *plan) {
   const size_t o1 = push_i(t->down_first), o2 = push_i(t->down_nw), o3 = push_f(t->down_w),
                o4 = push_f(t->lags), o5 = push_f(t->pen), o6 = push_i(t->up_first), o7 = push_i(t->up_nw),
                o8 = push_f(t->up_w);
+  const size_t o9 = blob.size();
+  blob.resize(o9 + t->up_w_t.size() * 2);
+  std::memcpy(blob.data() + o9, t->up_w_t.data(), t->up_w_t.size() * 8);
   int32_t *d = nullptr;
   cudaError_t e = cudaMalloc(&d, blob.size() * 4);
   if (e == cudaSuccess) e = upload(d, blob.data(), blob.size() * 4);
@@ -213,6 +229,7 @@ int pitch_plan_init(snb_plan *plan) {
   t->d_pen = reinterpret_cast<const float *>(d + o5);
   t->d_up_first = d + o6; t->d_up_nw = d + o7;
   t->d_up_w = reinterpret_cast<const float *>(d + o8);
+  t->d_up_w_t = reinterpret_cast<const double *>(d + o9);
   return SNB_OK;
 }
 
@@ -223,7 +240,11 @@ void pitch_plan_free(snb_plan *plan) {
   plan->pitch = nullptr;
 }
 
-// per-utterance phase info packed as int64 x 4: down_offset, m1, m2, end1
+// per-utterance phase info packed as int64 x 4: down_offset, m1, m2, end1,
+// followed by order[nutts] (utterances by decreasing number of frames, stable:
+// the identity for equal lengths) and gfo[nutts+1] (frames cumulated in that
+// order): the frame-parallel kernel and the tracker walk the batch in this
+// order so that the utterances of a tracker wave have similar lengths
 int pitch_batch_init(const snb_plan *plan, snb_batch *b) {
   const snb_pitch_opts &o = plan->po;
   const PitchTables *t = plan->pitch;
@@ -240,12 +261,27 @@ int pitch_batch_init(const snb_plan *plan, snb_batch *b) {
   }
   info[4 * b->nutts] = off;
   b->total_down = off;
+  std::vector<int64_t> order(static_cast<size_t>(b->nutts));
+  for (int64_t u = 0; u < b->nutts; ++u) order[u] = u;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+    return b->frame_offsets[x + 1] - b->frame_offsets[x] > b->frame_offsets[y + 1] - b->frame_offsets[y];
+  });
+  info.insert(info.end(), order.begin(), order.end());
+  int64_t acc = 0;
+  info.push_back(0);
+  for (int64_t k = 0; k < b->nutts; ++k) {
+    acc += b->frame_offsets[order[k] + 1] - b->frame_offsets[order[k]];
+    info.push_back(acc);
+  }
   b->down_offsets = info;       // uploaded by snb_batch_create with the other tables
   return SNB_OK;
 }
 
+
 // ---------------------------------------------------------------------------
-// k1: LinearResample::Resample for the whole batch
+// k1: LinearResample::Resample for the whole batch.  The sum runs in double
+// like the oracle's (weight x int16 sample is exact in double, so one DFMA per
+// tap is the oracle's "exact product, rounded add"), rounded to float once.
 // ---------------------------------------------------------------------------
 struct ResampleArgs {
   const int16_t *pcm;
@@ -292,297 +328,299 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
   const int32_t wrapped = static_cast<int32_t>(so - unit * a.out_unit);
   const int64_t first_in = a.first[wrapped] + unit * a.in_unit;
   const float *w = a.w + static_cast<int64_t>(wrapped) * a.nw_max;
-  float acc = 0.0f;
+  double acc = 0.0;
   const int32_t nw = a.nw[wrapped];
   for (int32_t j = 0; j < nw; ++j) {
     const int64_t k = first_in + j;
-    if (k >= 0 && k < n_in) acc = fmaf(w[j], static_cast<float>(a.pcm[in0 + k]), acc);
+    if (k >= 0 && k < n_in)
+      acc = fma(static_cast<double>(w[j]), static_cast<double>(a.pcm[in0 + k]), acc);
   }
-  a.down[idx] = acc;
+  a.down[idx] = static_cast<float>(acc);
 }
 
 // ---------------------------------------------------------------------------
-// k2: per-utterance NCCF + Viterbi
+// k2: NCCF ballast of every utterance.  Kaldi's online class normalises with
+// the mean square of the downsampled signal "seen so far": offline that is
+// two values, before and after the resampler is flushed.
+// One CTA per utterance, double sums, fixed reduction order.
 // ---------------------------------------------------------------------------
-struct TrackArgs {
+struct BallastArgs {
   const float *down;
   const int64_t *info;
-  const int64_t *frame_offsets;
-  int64_t nutts;
-  int32_t first_lag, nmeas, nstates, shift, basic_len, full_len, up_nw_max;
-  int32_t snip_edges;
-  float preemph, soft_min_f0, nccf_ballast;
-  const float *lags, *pen, *up_w;
-  const int32_t *up_first, *up_nw;
-  // per-CTA scratch
-  int16_t *bp;            // [grid, max_frames, nstates]
-  float *pov_raw;         // [grid, max_frames, nmeas]
-  int32_t *states;        // [grid, max_frames]
-  int64_t max_frames;
-  float *out;
-  int64_t ld_out;
-  unsigned long long *queue;   // warp tracker: next utterance to hand out (zeroed before the launch)
+  int32_t basic_len;
+  float nccf_ballast;
+  float *ballast;               // [nutts, 2]
 };
 
-__device__ __forceinline__ double block_sum_f64(double v, double *s_red) {
+__global__ void __launch_bounds__(256) pitch_ballast_kernel(const BallastArgs a) {
+  __shared__ double s_red[4][8];
+  const int64_t u = blockIdx.x;
+  const int64_t doff = a.info[4 * u], m1 = a.info[4 * u + 1], m2 = a.info[4 * u + 2];
+  const float *x = a.down + doff;
+  double p1 = 0.0, q1 = 0.0, p2 = 0.0, q2 = 0.0;
+  for (int64_t i = threadIdx.x; i < m2; i += blockDim.x) {
+    const double v = x[i];
+    if (i < m1) { p1 += v; q1 = fma(v, v, q1); } else { p2 += v; q2 = fma(v, v, q2); }
+  }
+  p1 = group_sum_f64<32>(p1); q1 = group_sum_f64<32>(q1);
+  p2 = group_sum_f64<32>(p2); q2 = group_sum_f64<32>(q2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = group_sum_f64<32>(v);
+  if (lane == 0) { s_red[0][warp] = p1; s_red[1][warp] = q1; s_red[2][warp] = p2; s_red[3][warp] = q2; }
   __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < kPitchThreads / 32; ++w) t += s_red[w];
-  return t;
+  if (threadIdx.x == 0) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < 4; ++k)
+      for (int w = 0; w < 8; ++w) t[k] += s_red[k][w];
+    const double sum1 = t[0], sq1 = t[1], sum2 = t[0] + t[2], sq2 = t[1] + t[3];
+    const double n1 = static_cast<double>(m1), n2 = static_cast<double>(m2);
+    const double ms1 = m1 > 0 ? sq1 / n1 - (sum1 / n1) * (sum1 / n1) : 0.0;
+    const double ms2 = m2 > 0 ? sq2 / n2 - (sum2 / n2) * (sum2 / n2) : 0.0;
+    a.ballast[2 * u] = static_cast<float>((ms1 * a.basic_len) * (ms1 * a.basic_len) *
+                                           static_cast<double>(a.nccf_ballast));
+    a.ballast[2 * u + 1] = static_cast<float>((ms2 * a.basic_len) * (ms2 * a.basic_len) *
+                                               static_cast<double>(a.nccf_ballast));
+  }
 }
 
-#ifndef SNB_PITCH_MINB
-#define SNB_PITCH_MINB 4
-#endif
-__global__ void __launch_bounds__(kPitchThreads, SNB_PITCH_MINB) pitch_track_kernel(const TrackArgs a) {
+// ---------------------------------------------------------------------------
+// k3: frame-parallel front end of the tracker.  Everything of a frame that does
+// not depend on the previous frame -- ExtractFrame, mean removal, NCCF at the
+// integer lags (pitch and POV flavours), sinc upsampling to the log-spaced lags
+// and the local cost of every Viterbi state -- for ALL frames of a group of
+// utterances at full occupancy (round 1 ran this inside the sequential
+// warp-per-utterance loop: 26 % of its instructions).
+//
+// One warp per frame, tasks of kNccfTask consecutive frames.  Every dot
+// product accumulates in double in index order, exactly like the oracle's
+// dotf() (oracle/kaldi_oracle.c), and is rounded to float once: the local
+// costs, hence the Viterbi state sequence, are bit-identical to the oracle's.
+//
+// Outputs: cost [group_frames, ns4] float32 (row stride ns4 = ns rounded up to
+// 4: rows are 16-byte aligned for the tracker's cp.async), pov [group_frames, nm].
+// ---------------------------------------------------------------------------
+constexpr int kNccfTask = 8;
+
+struct NccfArgs {
+  const float *down;
+  const int64_t *info;          // [nutts,4]
+  const int64_t *order;         // [nutts] utterances by decreasing number of frames
+  const int64_t *gfo;           // [nutts+1] cumulated frames in that order
+  const float *ballast;         // [nutts,2]
+  int64_t k0, k1, q0, q1;       // group: sorted utterances [k0,k1), frames [q0,q1)
+  int32_t first_lag, nmeas, nstates, ns4, shift, basic_len, full_len, nw, ns_pad;
+  int32_t snip_edges, table_in_smem;
+  float preemph, soft_min_f0;
+  const float *lags;
+  const double *up_w_t;         // [nw, ns_pad] taps, state-contiguous
+  const int32_t *up_first;
+  float *cost, *pov;
+};
+
+struct NccfSmem {               // per-warp offsets in doubles
+  int z, pre, np, total;
+};
+__host__ __device__ inline NccfSmem nccf_smem_layout(int full_len, int nm, int nw) {
+  NccfSmem s;
+  int off = 0;
+  s.z = off; off += (full_len + 6 + 1) & ~1;      // zero tail read by the sliding NCCF loop
+  s.pre = off; off += (full_len + 2 + 1) & ~1;
+  s.np = off; off += (nm + nw + 1 + 1) & ~1;      // zero tail for the padded taps
+  s.total = off;
+  return s;
+}
+__host__ __device__ inline int nccf_shared_words(int ns, int ns_pad, int nw, bool table) {
+  return (table ? 2 * nw * ns_pad : 0) + 2 * ((ns + 1) & ~1);   // taps (doubles), up_first, soft_min_f0*lag
+}
+
+__global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_win = reinterpret_cast<float *>(smem_raw);          // [full_len]
-  float *s_np = s_win + a.full_len;                             // nccf_pitch [nmeas]
-  float *s_nv = s_np + a.nmeas;                                 // nccf_pov   [nmeas]
-  float *s_prev = s_nv + a.nmeas;                               // forward cost [nstates]
-  float *s_new = s_prev + a.nstates;
-  float *s_pen = s_new + a.nstates;
-  float *s_lags = s_pen + a.nstates;
-  float *s_upw = s_lags + a.nstates;                            // [nstates, up_nw_max]
-  int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + a.nstates * a.up_nw_max);
-  int32_t *s_upn = s_upfirst + a.nstates;
-  __shared__ double s_red[kPitchThreads / 32];
-  __shared__ int s_abp[kPitchThreads * kMaxStatesPerThread / 16 + 2];
-  __shared__ float s_acost[kPitchThreads * kMaxStatesPerThread / 16 + 2];
-  __shared__ float s_fred[kPitchThreads / 32];
-  __shared__ int s_ired[kPitchThreads / 32];
-  __shared__ float s_scalar[4];
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ns = a.nstates, nm = a.nmeas;
-  for (int i = tid; i < ns; i += kPitchThreads) {
-    s_pen[i] = a.pen[i];
-    s_lags[i] = a.lags[i];
-    s_upfirst[i] = a.up_first[i];
-    s_upn[i] = a.up_nw[i];
+  const int nwarp_cta = blockDim.x >> 5;
+  const int ns = a.nstates, nm = a.nmeas, bl = a.basic_len, fl = a.full_len, nw = a.nw;
+  // ---- CTA-shared tables ----
+  double *s_upw = reinterpret_cast<double *>(smem_raw);
+  const int tab_words = a.table_in_smem ? 2 * nw * a.ns_pad : 0;
+  int32_t *s_upfirst = reinterpret_cast<int32_t *>(smem_raw) + tab_words;
+  float *s_lagc = reinterpret_cast<float *>(s_upfirst + ((ns + 1) & ~1));
+  if (a.table_in_smem)
+    for (int i = tid; i < nw * a.ns_pad; i += blockDim.x) s_upw[i] = a.up_w_t[i];
+  for (int i = tid; i < ns; i += blockDim.x) {
+    s_upfirst[i] = min(max(a.up_first[i], 0), nm - 1);       // (a state without taps has zero weights)
+    s_lagc[i] = __fmul_rn(a.soft_min_f0, a.lags[i]);
   }
-  for (int i = tid; i < ns * a.up_nw_max; i += kPitchThreads) s_upw[i] = a.up_w[i];
   __syncthreads();
+  const double *upw = a.table_in_smem ? s_upw : a.up_w_t;
+  // ---- warp-private buffers ----
+  const NccfSmem L = nccf_smem_layout(fl, nm, nw);
+  double *wbase = reinterpret_cast<double *>(smem_raw + 4 * static_cast<size_t>(nccf_shared_words(ns, a.ns_pad, nw, a.table_in_smem))) +
+                  static_cast<size_t>(warp) * L.total;
+  double *w_z = wbase + L.z, *w_pre = wbase + L.pre, *w_np = wbase + L.np;
+  for (int i = fl + lane; i < fl + 6; i += 32) w_z[i] = 0.0;
+  for (int i = nm + lane; i < nm + nw + 1; i += 32) w_np[i] = 0.0;
 
-  int16_t *bp = a.bp + static_cast<int64_t>(blockIdx.x) * a.max_frames * ns;
-  float *pov_raw = a.pov_raw + static_cast<int64_t>(blockIdx.x) * a.max_frames * nm;
-  int32_t *states = a.states + static_cast<int64_t>(blockIdx.x) * a.max_frames;
-
-  for (int64_t u = blockIdx.x; u < a.nutts; u += gridDim.x) {
-    const int64_t doff = a.info[4 * u], m1 = a.info[4 * u + 1], m2 = a.info[4 * u + 2],
-                  end1 = a.info[4 * u + 3];
-    const int64_t row0 = a.frame_offsets[u], F = a.frame_offsets[u + 1] - row0;
-    if (F <= 0) continue;
-    const float *x = a.down + doff;
-    // ---- global mean-square for the ballast (double sums, two phases) ----
-    double p1 = 0.0, q1 = 0.0, p2 = 0.0, q2 = 0.0;
-    for (int64_t i = tid; i < m2; i += kPitchThreads) {
-      const double v = x[i];
-      if (i < m1) { p1 += v; q1 += v * v; } else { p2 += v; q2 += v * v; }
+  const int64_t ntasks = (a.q1 - a.q0 + kNccfTask - 1) / kNccfTask;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * nwarp_cta + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * nwarp_cta;
+  for (int64_t task = gw; task < ntasks; task += nwarps) {
+    const int64_t qa = a.q0 + task * kNccfTask, qb = min(qa + kNccfTask, a.q1);
+    // utterance (in sorted order) of the task's first frame: equal-length guess, else bisection
+    int64_t k;
+    {
+      k = a.k0 + static_cast<int64_t>(static_cast<double>(qa - a.q0) * static_cast<double>(a.k1 - a.k0) /
+                                      static_cast<double>(a.q1 - a.q0));
+      k = min(max(k, a.k0), a.k1 - 1);
+      if (!(a.gfo[k] <= qa && qa < a.gfo[k + 1])) {
+        int64_t lo = a.k0, hi = a.k1;
+        while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (a.gfo[mid] <= qa) lo = mid; else hi = mid;
+        }
+        k = lo;
+      }
     }
-    const double sum1 = block_sum_f64(p1, s_red), sq1 = block_sum_f64(q1, s_red);
-    const double sum2 = sum1 + block_sum_f64(p2, s_red), sq2 = sq1 + block_sum_f64(q2, s_red);
-    const double ms1 = m1 > 0 ? sq1 / static_cast<double>(m1) - (sum1 / static_cast<double>(m1)) * (sum1 / static_cast<double>(m1)) : 0.0;
-    const double ms2 = m2 > 0 ? sq2 / static_cast<double>(m2) - (sum2 / static_cast<double>(m2)) * (sum2 / static_cast<double>(m2)) : 0.0;
-    const float ballast1 = static_cast<float>((ms1 * a.basic_len) * (ms1 * a.basic_len) * static_cast<double>(a.nccf_ballast));
-    const float ballast2 = static_cast<float>((ms2 * a.basic_len) * (ms2 * a.basic_len) * static_cast<double>(a.nccf_ballast));
-    for (int i = tid; i < ns; i += kPitchThreads) s_prev[i] = 0.0f;
-    __syncthreads();
-
-    for (int64_t f = 0; f < F; ++f) {
+    int64_t kcur = -1, doff = 0, m1 = 0, m2 = 0, end1 = 0, fbase = 0;
+    float ballast1 = 0.0f, ballast2 = 0.0f;
+    for (int64_t q = qa; q < qb; ++q) {
+      while (a.gfo[k + 1] <= q) ++k;
+      if (k != kcur) {
+        kcur = k;
+        const int64_t u = a.order[k];
+        doff = a.info[4 * u]; m1 = a.info[4 * u + 1]; m2 = a.info[4 * u + 2]; end1 = a.info[4 * u + 3];
+        ballast1 = a.ballast[2 * u]; ballast2 = a.ballast[2 * u + 1];
+        fbase = a.gfo[k];
+      }
+      const int64_t f = q - fbase;
       const bool phase2 = f >= end1;
       const int64_t avail = phase2 ? m2 : m1;
       const float ballast = phase2 ? ballast2 : ballast1;
+      const float *x = a.down + doff;
       int64_t start;
       if (a.snip_edges) start = f * a.shift;
-      else start = static_cast<int64_t>((static_cast<double>(f) + 0.5) * a.shift) - a.full_len / 2;
-      // ---- ExtractFrame (zeros outside the available signal) ----
-      for (int i = tid; i < a.full_len; i += kPitchThreads) {
-        const int64_t k = start + i;
-        s_win[i] = (k >= 0 && k < avail) ? x[k] : 0.0f;
+      else start = static_cast<int64_t>((static_cast<double>(f) + 0.5) * a.shift) - fl / 2;
+      // ---- ExtractFrame (zeros beyond the available signal), optional pre-emphasis ----
+      __syncwarp();
+      if (a.preemph == 0.0f) {
+        double s = 0.0;
+        for (int i = lane; i < fl; i += 32) {
+          const int64_t kk = start + i;
+          const float v = (kk >= 0 && kk < avail) ? x[kk] : 0.0f;
+          w_z[i] = static_cast<double>(v);
+          if (i < bl) s += static_cast<double>(v);
+        }
+        const float mean = static_cast<float>(group_sum_f64<32>(s) / static_cast<double>(bl));
+        __syncwarp();
+        for (int i = lane; i < fl; i += 32)
+          w_z[i] = static_cast<double>(__fadd_rn(static_cast<float>(w_z[i]), -mean));
+      } else {
+        // window[i] -= c * window[i-1] for i = fl-1 .. 1 (original neighbours), window[0] *= 1 - c
+        for (int i = lane; i < fl; i += 32) {
+          const int64_t kk = start + i;
+          w_pre[i] = static_cast<double>((kk >= 0 && kk < avail) ? x[kk] : 0.0f);
+        }
+        __syncwarp();
+        double s = 0.0;
+        for (int i = lane; i < fl; i += 32) {
+          const float cur = static_cast<float>(w_pre[i]);
+          float v;
+          if (i > 0) v = __fadd_rn(cur, -__fmul_rn(a.preemph, static_cast<float>(w_pre[i - 1])));
+          else v = __fmul_rn(cur, static_cast<float>(1.0 - static_cast<double>(a.preemph)));
+          w_z[i] = static_cast<double>(v);
+          if (i < bl) s += static_cast<double>(v);
+        }
+        const float mean = static_cast<float>(group_sum_f64<32>(s) / static_cast<double>(bl));
+        __syncwarp();
+        for (int i = lane; i < fl; i += 32)
+          w_z[i] = static_cast<double>(__fadd_rn(static_cast<float>(w_z[i]), -mean));
       }
-      __syncthreads();
-      if (a.preemph != 0.0f) {
-        // window[i] -= c * window[i-1] (original values), window[0] *= (1 - c)
-        float vals[16];
-        int cnt = 0;
-        for (int i = tid; i < a.full_len && cnt < 16; i += kPitchThreads, ++cnt)
-          vals[cnt] = (i > 0) ? fmaf(-a.preemph, s_win[i - 1], s_win[i]) : s_win[0] * (1.0f - a.preemph);
-        __syncthreads();
-        cnt = 0;
-        for (int i = tid; i < a.full_len && cnt < 16; i += kPitchThreads, ++cnt) s_win[i] = vals[cnt];
-        __syncthreads();
+      __syncwarp();
+      // ---- double prefix sums of squares: pre[k] = sum_{i<k} z_i^2 (every lag's window energy
+      //      is a difference of two entries) ----
+      {
+        const int chunk = (fl + 31) / 32;
+        const int i0 = min(lane * chunk, fl), i1 = min(fl, i0 + chunk);
+        double local = 0.0;
+        for (int i = i0; i < i1; ++i) local = fma(w_z[i], w_z[i], local);
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(SNB_FULL_MASK, incl, o);
+          if (lane >= o) incl += up;
+        }
+        double run = incl - local;
+        for (int i = i0; i < i1; ++i) {
+          w_pre[i] = run;
+          run = fma(w_z[i], w_z[i], run);
+        }
+        if (i1 == fl && i0 < fl) w_pre[fl] = run;
       }
-      // ---- ComputeCorrelation: subtract the mean of the first basic_len ----
-      if (warp == 0) {
-        float s = 0.0f;
-        for (int i = lane; i < a.basic_len; i += 32) s += s_win[i];
-        s = group_sum<32>(s);
-        if (lane == 0) s_scalar[0] = __fdiv_rn(s, static_cast<float>(a.basic_len));
-      }
-      __syncthreads();
-      const float mean = s_scalar[0];
-      for (int i = tid; i < a.full_len; i += kPitchThreads) s_win[i] -= mean;
-      __syncthreads();
-      if (warp == 0) {
-        float e = 0.0f;
-        for (int i = lane; i < a.basic_len; i += 32) e = fmaf(s_win[i], s_win[i], e);
-        e = group_sum<32>(e);
-        if (lane == 0) s_scalar[1] = e;
-      }
-      __syncthreads();
-      const float e1 = s_scalar[1];
-      // ---- NCCF at the integer lags: 2 threads per lag ----
-      for (int l0 = 0; l0 < nm; l0 += kPitchThreads / 2) {
-        const int l = l0 + (tid >> 1), part = tid & 1;
-        float e2 = 0.0f, inner = 0.0f;
-        if (l < nm) {
-          const int lag = a.first_lag + l;
-          const int half = (a.basic_len + 1) / 2;
-          const int i0 = part * half, i1 = min(a.basic_len, i0 + half);
-          for (int i = i0; i < i1; ++i) {
-            const float v = s_win[lag + i];
-            e2 = fmaf(v, v, e2);
-            inner = fmaf(s_win[i], v, inner);
+      __syncwarp();
+      const float e1 = static_cast<float>(w_pre[bl]);
+      const int64_t qrel = q - a.q0;
+      // ---- NCCF at the integer lags: a lane owns three consecutive lags, the lagged samples
+      //      slide through six registers (2 + 4 LDS.64 per 12 DFMA) ----
+#pragma unroll 1
+      for (int lb = 0; lb < nm; lb += 96) {
+        const int l0 = lb + 3 * lane;
+        const double *zq = w_z + a.first_lag + min(l0, nm - 1);    // (reads up to 5 doubles of zero tail)
+        double in0 = 0.0, in1 = 0.0, in2 = 0.0;
+        double r0 = zq[0], r1 = zq[1];
+        int i = 0;
+#pragma unroll 1
+        for (; i + 3 < bl; i += 4) {
+          const double2 wa = *reinterpret_cast<const double2 *>(w_z + i);
+          const double2 wb = *reinterpret_cast<const double2 *>(w_z + i + 2);
+          const double r2 = zq[i + 2], r3 = zq[i + 3], r4 = zq[i + 4], r5 = zq[i + 5];
+          in0 = fma(wa.x, r0, in0); in1 = fma(wa.x, r1, in1); in2 = fma(wa.x, r2, in2);
+          in0 = fma(wa.y, r1, in0); in1 = fma(wa.y, r2, in1); in2 = fma(wa.y, r3, in2);
+          in0 = fma(wb.x, r2, in0); in1 = fma(wb.x, r3, in1); in2 = fma(wb.x, r4, in2);
+          in0 = fma(wb.y, r3, in0); in1 = fma(wb.y, r4, in1); in2 = fma(wb.y, r5, in2);
+          r0 = r4; r1 = r5;
+        }
+        for (; i < bl; ++i) {
+          const double wv = w_z[i];
+          in0 = fma(wv, zq[i], in0); in1 = fma(wv, zq[i + 1], in1); in2 = fma(wv, zq[i + 2], in2);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const int l = l0 + kk;
+          const float inner = static_cast<float>(kk == 0 ? in0 : (kk == 1 ? in1 : in2));
+          if (l < nm) {
+            const int lag = a.first_lag + l;
+            const float e2 = static_cast<float>(w_pre[lag + bl] - w_pre[lag]);
+            const float norm = __fmul_rn(e1, e2);
+            const float den_p = __fsqrt_rn(__fadd_rn(norm, ballast));
+            const float den_v = __fsqrt_rn(norm);
+            w_np[l] = static_cast<double>(den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f);
+            a.pov[qrel * nm + l] = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
           }
         }
-        e2 += __shfl_xor_sync(SNB_FULL_MASK, e2, 1);
-        inner += __shfl_xor_sync(SNB_FULL_MASK, inner, 1);
-        if (l < nm && part == 0) {
-          const float norm = __fmul_rn(e1, e2);
-          const float den_p = sqrtf(__fadd_rn(norm, ballast));
-          const float den_v = sqrtf(norm);
-          s_np[l] = den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f;
-          const float pv = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
-          s_nv[l] = pv;
-          pov_raw[f * nm + l] = pv;
-        }
       }
-      __syncthreads();
-      // ---- upsample nccf_pitch to the log-spaced lags; local cost ----
-      for (int i = tid; i < ns; i += kPitchThreads) {
-        const float *w = s_upw + i * a.up_nw_max;
-        const int first = s_upfirst[i], n = s_upn[i];
-        float acc = 0.0f;
-        for (int j = 0; j < n; ++j) acc = fmaf(w[j], s_np[first + j], acc);
-        // local_cost = 1 - nccf; += soft_min_f0 * lag * nccf
-        float c = __fadd_rn(1.0f, -acc);
-        c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
-        s_new[i] = c;                  // holds the local cost until the state is finalised
+      __syncwarp();
+      // ---- upsample to the log-spaced lags (taps padded with zero weights to nw); local cost ----
+      float *crow = a.cost + qrel * a.ns4;
+      for (int i = lane; i < ns; i += 32) {
+        const double *src = w_np + s_upfirst[i];
+        const double *w = upw + i;
+        double acc = 0.0;
+#pragma unroll 5
+        for (int j = 0; j < nw; ++j) acc = fma(w[static_cast<size_t>(j) * a.ns_pad], src[j], acc);
+        const float nccf = static_cast<float>(acc);
+        // local_cost = 1 - nccf; local_cost += soft_min_f0 * lag * nccf
+        float c = __fadd_rn(1.0f, -nccf);
+        c = __fadd_rn(__fmul_rn(s_lagc[i], nccf), c);
+        crow[i] = c;
       }
-      // ---- exact Viterbi step: min_j pen[|i-j|] + prev[j] (first minimal j) ----
-      // The transition cost is convex in (i - j), so the minimising j is
-      // non-decreasing in i (Monge property).  Level 1: every kAnchor-th state
-      // (and the last one) scans all j, one warp per anchor.  Level 2: every
-      // other state scans only [bp(left anchor), bp(right anchor)].  ~10x fewer
-      // evaluations than the full 417 x 417 scan, same minimum.
-      constexpr int kAnchor = 16;
-      const int nanchor = (ns - 1 + kAnchor - 1) / kAnchor + 1;     // 0, 16, ..., ns-1
-      for (int t = warp; t < nanchor; t += kPitchThreads / 32) {
-        const int i = min(t * kAnchor, ns - 1);
-        float best = FLT_MAX;
-        int bj = 0x7fffffff;
-        for (int j = lane; j < ns; j += 32) {
-          const int d = j > i ? j - i : i - j;
-          const float c = __fadd_rn(s_pen[d], s_prev[j]);
-          if (c < best) { best = c; bj = j; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(SNB_FULL_MASK, best, o);
-          const int oj = __shfl_xor_sync(SNB_FULL_MASK, bj, o);
-          if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
-        }
-        if (lane == 0) { s_abp[t] = bj; s_acost[t] = best; }
-      }
-      __syncthreads();
-      float lmin = FLT_MAX;
-      for (int i = tid; i < ns; i += kPitchThreads) {
-        const int ta = i / kAnchor;
-        float best;
-        int bj;
-        if (i == ta * kAnchor || i == ns - 1) {
-          const int t = (i == ns - 1) ? nanchor - 1 : ta;
-          best = s_acost[t]; bj = s_abp[t];
-        } else {
-          const int ja = s_abp[ta], jb = s_abp[min(ta + 1, nanchor - 1)];
-          const int jlo = min(ja, jb), jhi = max(ja, jb);
-          best = FLT_MAX; bj = jlo;
-          for (int j = jlo; j <= jhi; ++j) {
-            const int d = j > i ? j - i : i - j;
-            const float c = __fadd_rn(s_pen[d], s_prev[j]);
-            if (c < best) { best = c; bj = j; }
-          }
-        }
-        bp[f * ns + i] = static_cast<int16_t>(bj);
-        const float v = __fadd_rn(best, s_new[i]);      // + local cost (own slot)
-        s_new[i] = v;
-        lmin = fminf(lmin, v);
-      }
-      // block min -> renormalise so the smallest forward cost is zero
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(SNB_FULL_MASK, lmin, o));
-      if (lane == 0) s_fred[warp] = lmin;
-      __syncthreads();
-      float gmin = s_fred[0];
-      for (int w = 1; w < kPitchThreads / 32; ++w) gmin = fminf(gmin, s_fred[w]);
-      for (int i = tid; i < ns; i += kPitchThreads) s_prev[i] = __fadd_rn(s_new[i], -gmin);
-      __syncthreads();
     }
-    // ---- best final state (first minimum) and backtrace ----
-    {
-      float best = FLT_MAX;
-      int bi = 0x7fffffff;
-      for (int i = tid; i < ns; i += kPitchThreads)
-        if (s_prev[i] < best) { best = s_prev[i]; bi = i; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(SNB_FULL_MASK, best, o);
-        const int oi = __shfl_xor_sync(SNB_FULL_MASK, bi, o);
-        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (lane == 0) { s_fred[warp] = best; s_ired[warp] = bi; }
-      __syncthreads();
-      if (tid == 0) {
-        float b = s_fred[0];
-        int s = s_ired[0];
-        for (int w = 1; w < kPitchThreads / 32; ++w)
-          if (s_fred[w] < b || (s_fred[w] == b && s_ired[w] < s)) { b = s_fred[w]; s = s_ired[w]; }
-        for (int64_t f = F - 1; f >= 0; --f) {
-          states[f] = s;
-          s = bp[f * ns + s];
-        }
-      }
-      __syncthreads();
-      __threadfence_block();
-    }
-    // ---- output rows: (NCCF_pov at the chosen lag, 1 / lag) ----
-    for (int64_t f = tid; f < F; f += kPitchThreads) {
-      const int s = states[f];
-      const float *w = s_upw + s * a.up_nw_max;
-      const float *pv = pov_raw + f * nm + s_upfirst[s];
-      float acc = 0.0f;
-      for (int j = 0; j < s_upn[s]; ++j) acc = fmaf(w[j], pv[j], acc);
-      float *o = a.out + (row0 + f) * a.ld_out;
-      o[0] = acc;
-      o[1] = __fdiv_rn(1.0f, s_lags[s]);
-    }
-    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------
-// k2': warp-per-utterance tracker (default).  Same arithmetic as
-// pitch_track_kernel, but each warp owns one utterance: no block barriers in
-// the frame loop (only __syncwarp), up to 24 independent utterances per CTA
-// (one CTA per SM, tables shared), utterances handed out through an atomic
-// queue, window energies from a double prefix sum (one pass instead of one per
-// lag), three NCCF lags per lane in flight, and a monotone divide-and-conquer
-// Viterbi step.
+// k4: Viterbi over the frames of an utterance, one WARP per utterance (the
+// recursion is sequential in time: the parallelism is utterances).  Reads the
+// local costs of k3 (next frame's row prefetched with cp.async while the
+// current step runs), keeps the forward costs in the warp's shared memory,
+// writes int16 backpointers to a per-warp global scratch, then backtraces and
+// emits (NCCF_pov at the chosen lag, 1 / lag).
 //
 // Viterbi step: bp(i) = first argmin_j pen[|i-j|] + prev[j] is non-decreasing
 // in i (the penalty is convex), so bp(i) lies in [bp(i-s), bp(i+s)].
@@ -594,9 +632,11 @@ __global__ void __launch_bounds__(kPitchThreads, SNB_PITCH_MINB) pitch_track_ker
 //     follows i; the few states that straddle a jump of bp (range > 2s+2) are
 //     handed to whole-warp scans instead of stalling their round.
 // Every scan keeps the first minimum of its range, exactly like the
-// brute-force reference step (oracle/kaldi_oracle.c, orc_compute_pitch).
+// brute-force step (and like Kaldi's bound-tightening search, which the oracle
+// restates: checked equal on 834 000 states in round 1).
 // ---------------------------------------------------------------------------
-constexpr int kTrackWarpsMax = 20;   // (24 fit in shared memory but run erratically slower)
+constexpr int kTrackWarpsMax = 28;
+constexpr int kTrackWarpsMin = 4;
 #ifndef SNB_PITCH_A1LOG2
 #define SNB_PITCH_A1LOG2 6
 #endif
@@ -605,29 +645,30 @@ constexpr int kTrackWarpsMax = 20;   // (24 fit in shared memory but run erratic
 #endif
 constexpr int kA1Log2 = SNB_PITCH_A1LOG2, kA1 = 1 << kA1Log2;
 
-struct WarpSmem {           // per-warp float offsets
-  int win, pre, np, nv, prev, cost, abp, total;
+struct TrackArgs {
+  const float *cost, *pov;
+  const int64_t *order, *gfo, *frame_offsets;
+  int64_t k0, k1, q0;
+  int32_t nstates, ns4, nmeas, nw, ns_pad;
+  const float *lags, *pen;
+  const double *up_w_t;
+  const int32_t *up_first;
+  int16_t *bp;            // [slots, max_frames, nstates]
+  int32_t *states;        // [slots, max_frames]
+  int64_t max_frames;
+  float *out;
+  int64_t ld_out;
+  unsigned long long *queue;   // next utterance to hand out (zeroed before the launch)
 };
 
 // backpointers of the current frame are read with strides 2s: skew the index
 __host__ __device__ inline int bp_slot(int i) { return i + (i >> 5); }
 
-__host__ __device__ inline WarpSmem warp_smem_layout(int full_len, int nm, int ns, int nw_max) {
-  WarpSmem w;
-  int off = 0;
-  w.win = off; off += (full_len + 4 + 3) / 4 * 4;             // + padding read by the NCCF loop
-  w.pre = off; off += 2 * ((full_len + 1 + 1) / 2 * 2);      // doubles (as float pairs)
-  w.np = off; off += (nm + nw_max + 3) / 4 * 4;               // + zero tail for the padded taps
-  w.nv = off; off += (nm + 3) / 4 * 4;
-  w.prev = off; off += (ns + 3) / 4 * 4;
-  w.cost = off; off += (ns + 3) / 4 * 4;
-  w.abp = off; off += (bp_slot(ns) + 4) / 4 * 4;              // int backpointers of this frame
-  w.total = (off + 3) / 4 * 4;
-  return w;
+__host__ __device__ inline int track_warp_words(int ns4, int ns) {
+  return 3 * ns4 + ((bp_slot(ns) + 4) & ~3);     // prev | cur | next cost rows, backpointers
 }
-
-__host__ __device__ inline int warp_shared_floats(int ns, int nw_max) {
-  return ((3 * ns + ns * (nw_max | 1) + ns) + 3) / 4 * 4;     // pen (mirrored), lags, up_w (odd row stride), up_first
+__host__ __device__ inline int track_shared_words(int ns) {
+  return (2 * ns + 3) & ~3;                       // penalties mirrored around the centre
 }
 
 // first argmin over j in [jlo, jhi] of pen[|i-j|] + prev[j], by the whole warp.
@@ -658,182 +699,56 @@ __device__ __forceinline__ void warp_argmin(float &best, int &bj) {
   }
 }
 
-template <int NWC>   // NWC > 0: number of upsampling taps known at compile time
-__global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kernel(const TrackArgs a) {
+// one 16-byte cp.async per lane and round: row [ns4] floats, global -> shared
+__device__ __forceinline__ void prefetch_row(float *dst, const float *src, int ns4, int lane) {
+  for (int i = 4 * lane; i < ns4; i += 128)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + i)), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_viterbi_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarp_cta = blockDim.x >> 5;
-  const int ns = a.nstates, nm = a.nmeas, bl = a.basic_len, fl = a.full_len;
-  const int nw = NWC > 0 ? NWC : a.up_nw_max;
-  const int nwp = nw | 1;                                     // odd row stride: conflict-free
-  // ---- CTA-shared tables ----
+  const int ns = a.nstates, ns4 = a.ns4, nm = a.nmeas, nw = a.nw;
   // penalty table mirrored around s_pen: s_pen[d] = pen[|d|], d in (-ns, ns):
   // the scans index it with the signed state distance, no absolute value
   float *s_pen = reinterpret_cast<float *>(smem_raw) + (ns - 1);
-  float *s_lags = reinterpret_cast<float *>(smem_raw) + 2 * ns;
-  float *s_upw = s_lags + ns;                                 // [ns][nwp]
-  int32_t *s_upfirst = reinterpret_cast<int32_t *>(s_upw + ns * nwp);
-  for (int i = tid; i < ns; i += blockDim.x) {
-    s_pen[i] = a.pen[i]; s_pen[-i] = a.pen[i]; s_lags[i] = a.lags[i];
-    s_upfirst[i] = min(max(a.up_first[i], 0), nm - 1);         // (a state without taps has zero weights)
-  }
-  for (int i = tid; i < ns * nw; i += blockDim.x) s_upw[(i / nw) * nwp + i % nw] = a.up_w[i];
+  for (int i = tid; i < ns; i += blockDim.x) { s_pen[i] = a.pen[i]; s_pen[-i] = a.pen[i]; }
   __syncthreads();
-  // ---- warp-private buffers ----
-  const WarpSmem L = warp_smem_layout(fl, nm, ns, nw);
-  float *wbase = reinterpret_cast<float *>(smem_raw) + warp_shared_floats(ns, nw) + warp * L.total;
-  float *w_win = wbase + L.win;
-  double *w_pre = reinterpret_cast<double *>(wbase + L.pre);
-  float *w_np = wbase + L.np, *w_nv = wbase + L.nv;
-  float *w_prev = wbase + L.prev, *w_cost = wbase + L.cost;
-  int *w_bp = reinterpret_cast<int *>(wbase + L.abp);
+  float *wbase = reinterpret_cast<float *>(smem_raw) + track_shared_words(ns) +
+                 static_cast<size_t>(warp) * track_warp_words(ns4, ns);
+  float *buf0 = wbase, *buf1 = wbase + ns4, *buf2 = wbase + 2 * ns4;
+  int *w_bp = reinterpret_cast<int *>(wbase + 3 * ns4);
 
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * nwarp_cta + warp;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * nwarp_cta;
   int16_t *bp = a.bp + gw * a.max_frames * ns;
-  float *pov_raw = a.pov_raw + gw * a.max_frames * nm;
   int32_t *states = a.states + gw * a.max_frames;
   const int n1 = (ns - 1 + kA1 - 1) / kA1 + 1;                // anchors min(t kA1, ns-1), t < n1
   int top = 1;
   while (top < n1) top <<= 1;
-  for (int i = nm + lane; i < nm + nw; i += 32) w_np[i] = 0.0f;
-  if (lane < 4) w_win[fl + lane] = 0.0f;
 
-  int64_t u = gw;
-  while (u < a.nutts) {
-    const int64_t doff = a.info[4 * u], m1 = a.info[4 * u + 1], m2 = a.info[4 * u + 2],
-                  end1 = a.info[4 * u + 3];
-    const int64_t row0 = a.frame_offsets[u], F = a.frame_offsets[u + 1] - row0;
-    const float *x = a.down + doff;
-    // ---- global mean-square for the ballast (double sums, two phases) ----
-    double p1 = 0.0, q1 = 0.0, p2 = 0.0, q2 = 0.0;
-    if (F > 0) {
-      for (int64_t i = lane; i < m2; i += 32) {
-        const double v = x[i];
-        if (i < m1) { p1 += v; q1 += v * v; } else { p2 += v; q2 += v * v; }
-      }
-    }
-    p1 = group_sum_f64<32>(p1); q1 = group_sum_f64<32>(q1);
-    p2 = group_sum_f64<32>(p2); q2 = group_sum_f64<32>(q2);
-    const double sum2 = p1 + p2, sq2 = q1 + q2;
-    const double ms1 = m1 > 0 ? q1 / static_cast<double>(m1) - (p1 / static_cast<double>(m1)) * (p1 / static_cast<double>(m1)) : 0.0;
-    const double ms2 = m2 > 0 ? sq2 / static_cast<double>(m2) - (sum2 / static_cast<double>(m2)) * (sum2 / static_cast<double>(m2)) : 0.0;
-    const float ballast1 = static_cast<float>((ms1 * bl) * (ms1 * bl) * static_cast<double>(a.nccf_ballast));
-    const float ballast2 = static_cast<float>((ms2 * bl) * (ms2 * bl) * static_cast<double>(a.nccf_ballast));
+  int64_t k = a.k0 + gw;
+  while (k < a.k1) {
+    const int64_t u = a.order[k];
+    const int64_t F = a.gfo[k + 1] - a.gfo[k];
+    const int64_t row0 = a.frame_offsets[u];
+    const float *crow = a.cost + (a.gfo[k] - a.q0) * ns4;
+    const float *prow = a.pov + (a.gfo[k] - a.q0) * nm;
+    float *w_prev = buf0, *w_cost = buf1, *w_next = buf2;
+    if (F > 0) prefetch_row(w_cost, crow, ns4, lane);
     for (int i = lane; i < ns; i += 32) w_prev[i] = 0.0f;
-    __syncwarp();
 
     for (int64_t f = 0; f < F; ++f) {
-      const bool phase2 = f >= end1;
-      const int64_t avail = phase2 ? m2 : m1;
-      const float ballast = phase2 ? ballast2 : ballast1;
-      int64_t start;
-      if (a.snip_edges) start = f * a.shift;
-      else start = static_cast<int64_t>((static_cast<double>(f) + 0.5) * a.shift) - fl / 2;
-      // ---- ExtractFrame ----
-      for (int i = lane; i < fl; i += 32) {
-        const int64_t k = start + i;
-        w_win[i] = (k >= 0 && k < avail) ? x[k] : 0.0f;
+      if (f + 1 < F) {
+        prefetch_row(w_next, crow + (f + 1) * ns4, ns4, lane);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncwarp();
-      if (a.preemph != 0.0f) {
-        for (int base = ((fl - 1) / 32) * 32; base >= 0; base -= 32) {   // downwards: original neighbours
-          const int i = base + lane;
-          float v = 0.0f;
-          if (i < fl) v = (i > 0) ? fmaf(-a.preemph, w_win[i - 1], w_win[i]) : w_win[0] * (1.0f - a.preemph);
-          __syncwarp();
-          if (i < fl) w_win[i] = v;
-          __syncwarp();
-        }
-      }
-      // ---- mean of the first basic_len samples, subtracted from the whole window ----
-      float sacc = 0.0f;
-      for (int i = lane; i < bl; i += 32) sacc += w_win[i];
-      const float mean = __fdiv_rn(group_sum<32>(sacc), static_cast<float>(bl));
-      // ---- zero-mean window + double prefix sums of squares: pre[k] = sum_{i<k} z_i^2 ----
-      {
-        const int chunk = (fl + 31) / 32;
-        const int i0 = lane * chunk, i1 = min(fl, i0 + chunk);
-        double local = 0.0;
-        for (int i = i0; i < i1; ++i) {
-          const float z = w_win[i] - mean;
-          w_win[i] = z;
-          local += static_cast<double>(z) * z;
-        }
-        double incl = local;                       // inclusive scan over lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double up = __shfl_up_sync(SNB_FULL_MASK, incl, o);
-          if (lane >= o) incl += up;
-        }
-        double run = incl - local;                 // exclusive
-        for (int i = i0; i < i1; ++i) {
-          w_pre[i] = run;
-          run += static_cast<double>(w_win[i]) * w_win[i];
-        }
-        if (i1 == fl && i0 < fl) w_pre[fl] = run;
-      }
-      __syncwarp();
-      const float e1 = static_cast<float>(w_pre[bl] - w_pre[0]);
-      // ---- NCCF at the integer lags: lane = three consecutive lags; the window
-      //      samples w[lag+i..] slide through six registers (4 new loads per 12 FMAs) ----
-#pragma unroll 1
-      for (int lb = 0; lb < nm; lb += 96) {
-        const int l0 = lb + 3 * lane;
-        const float *q = w_win + a.first_lag + min(l0, nm - 1);   // (reads up to 2 floats of padding)
-        float in0 = 0.0f, in1 = 0.0f, in2 = 0.0f;
-        float r0 = q[0], r1 = q[1];
-        int i = 0;
-#pragma unroll 1
-        for (; i + 3 < bl; i += 4) {
-          const float4 w4 = *reinterpret_cast<const float4 *>(w_win + i);
-          const float r2 = q[i + 2], r3 = q[i + 3], r4 = q[i + 4], r5 = q[i + 5];
-          in0 = fmaf(w4.x, r0, in0); in1 = fmaf(w4.x, r1, in1); in2 = fmaf(w4.x, r2, in2);
-          in0 = fmaf(w4.y, r1, in0); in1 = fmaf(w4.y, r2, in1); in2 = fmaf(w4.y, r3, in2);
-          in0 = fmaf(w4.z, r2, in0); in1 = fmaf(w4.z, r3, in1); in2 = fmaf(w4.z, r4, in2);
-          in0 = fmaf(w4.w, r3, in0); in1 = fmaf(w4.w, r4, in1); in2 = fmaf(w4.w, r5, in2);
-          r0 = r4; r1 = r5;
-        }
-        for (; i < bl; ++i) {
-          const float wv = w_win[i];
-          in0 = fmaf(wv, q[i], in0); in1 = fmaf(wv, q[i + 1], in1); in2 = fmaf(wv, q[i + 2], in2);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int l = l0 + k;
-          const float inner = k == 0 ? in0 : (k == 1 ? in1 : in2);
-          if (l < nm) {
-            const int lag = a.first_lag + l;
-            const float e2 = static_cast<float>(w_pre[lag + bl] - w_pre[lag]);
-            const float norm = __fmul_rn(e1, e2);
-            const float den_p = sqrtf(__fadd_rn(norm, ballast));
-            const float den_v = sqrtf(norm);
-            w_np[l] = den_p != 0.0f ? __fdiv_rn(inner, den_p) : 0.0f;
-            const float pv = den_v != 0.0f ? __fdiv_rn(inner, den_v) : 0.0f;
-            w_nv[l] = pv;
-            pov_raw[f * nm + l] = pv;
-          }
-        }
-      }
-      __syncwarp();
-      // ---- upsample to the log-spaced lags (taps padded with zeros to nw); local cost ----
-      for (int i = lane; i < ns; i += 32) {
-        const float *src = w_np + s_upfirst[i];
-        const float *w = s_upw + i * nwp;
-        float acc = 0.0f;
-        if (NWC > 0) {
-#pragma unroll
-          for (int j = 0; j < NWC; ++j) acc = fmaf(w[j], src[j], acc);
-        } else {
-#pragma unroll 4
-          for (int j = 0; j < nw; ++j) acc = fmaf(w[j], src[j], acc);
-        }
-        float c = __fadd_rn(1.0f, -acc);
-        c = __fadd_rn(__fmul_rn(__fmul_rn(a.soft_min_f0, s_lags[i]), acc), c);
-        w_cost[i] = c;
-      }
-      __syncwarp();
-      // ---- Viterbi step: anchors by whole-warp scans, bisection order ----
+      // ---- anchors by whole-warp scans, bisection order ----
       {
         const int last = ns - 1;
         int bj = coop_scan(s_pen, w_prev, 0, 0, last, lane);
@@ -863,9 +778,9 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
         const int T = min(SNB_PITCH_TMAX, 2 * s + 2);
 #pragma unroll 1
         for (int k0 = 0; k0 < nodd; k0 += 32) {
-          const int k = k0 + lane;
-          const bool act = k < nodd;
-          const int i = s * (2 * k + 1);
+          const int kk = k0 + lane;
+          const bool act = kk < nodd;
+          const int i = s * (2 * kk + 1);
           int jlo = 0, jhi = 0;
           if (act) {
             const int b0 = w_bp[bp_slot(i - s)], b1 = w_bp[bp_slot(min(i + s, ns - 1))];
@@ -911,8 +826,9 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(SNB_FULL_MASK, lmin, o));
       __syncwarp();
-      for (int i = lane; i < ns; i += 32) w_prev[i] = __fadd_rn(w_cost[i], -lmin);
+      for (int i = lane; i < ns; i += 32) w_cost[i] = __fadd_rn(w_cost[i], -lmin);
       __syncwarp();
+      float *t = w_prev; w_prev = w_cost; w_cost = w_next; w_next = t;
     }
     if (F > 0) {
       // ---- best final state (first minimum), backtrace, output rows ----
@@ -932,15 +848,17 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
       __threadfence_block();
       for (int64_t f = lane; f < F; f += 32) {
         const int sidx = states[f];
-        const float *w = s_upw + sidx * nwp;
-        const float *pv = pov_raw + f * nm + s_upfirst[sidx];
-        const int n = min(nw, nm - s_upfirst[sidx]);           // taps beyond are zero weights
-        float acc = 0.0f;
+        const int first = min(max(a.up_first[sidx], 0), nm - 1);
+        const double *w = a.up_w_t + sidx;
+        const float *pv = prow + f * nm + first;
+        const int n = min(nw, nm - first);                     // taps beyond are zero weights
+        double acc = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < n; ++j) acc = fmaf(w[j], pv[j], acc);
+        for (int j = 0; j < n; ++j)
+          acc = fma(w[static_cast<size_t>(j) * a.ns_pad], static_cast<double>(pv[j]), acc);
         float *o = a.out + (row0 + f) * a.ld_out;
-        o[0] = acc;
-        o[1] = __fdiv_rn(1.0f, s_lags[sidx]);
+        o[0] = static_cast<float>(acc);
+        o[1] = __fdiv_rn(1.0f, a.lags[sidx]);
       }
       __syncwarp();
     }
@@ -948,14 +866,17 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_track_warp_kerne
     unsigned long long nxt = 0;
     if (lane == 0) nxt = atomicAdd(a.queue, 1ULL);
     nxt = __shfl_sync(SNB_FULL_MASK, nxt, 0);
-    u = nwarps + static_cast<int64_t>(nxt);
+    k = a.k0 + nwarps + static_cast<int64_t>(nxt);
   }
 }
 
 // ---------------------------------------------------------------------------
-// k3: ProcessPitch (OnlineProcessPitch in offline use), delay == 0
-// grid = (nutts, chunks); each CTA owns kPostRows rows of one utterance plus
-// the halo the normalisation window needs
+// k5: ProcessPitch (OnlineProcessPitch in offline use).  Output row t of an
+// utterance holds the features of input frame max(0, t - delay); an utterance
+// of F > 0 frames gives F + delay rows (Kaldi's NumFramesReady once the input
+// is finished), written from row frame_offsets[u] + u * delay.
+// grid = (nutts, chunks); each CTA owns kPostRows output rows of one utterance
+// plus the halo the normalisation window needs
 // ---------------------------------------------------------------------------
 constexpr int kPostRows = 128;
 
@@ -964,6 +885,7 @@ struct PostArgs {
   const float *raw;
   int64_t ld_raw;
   const int64_t *frame_offsets;
+  const int64_t *out_offsets;   // optional output geometry (rows beyond it are dropped)
   uint64_t seed;
   float *out;
   int64_t ld_out;
@@ -983,17 +905,25 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
   extern __shared__ float s_post[];
   const int64_t u = blockIdx.x;
   const int64_t first = a.frame_offsets[u], F = a.frame_offsets[u + 1] - first;
+  const int64_t delay = a.o.delay;
+  int64_t Fo = F > 0 ? F + delay : 0;
+  int64_t first_out = first + u * delay;
+  if (a.out_offsets) {
+    first_out = a.out_offsets[u];
+    Fo = min(Fo, a.out_offsets[u + 1] - first_out);
+  }
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kPostRows;
-  if (r0 >= F) return;
+  if (r0 >= Fo) return;
   const int span = kPostRows + 2 * a.halo;
   float *s_logp = s_post, *s_pov = s_post + span;
-  const int64_t lo = r0 - a.halo;
+  const int64_t tb = r0 - delay;                                 // input frame of the CTA's first row
+  const int64_t lo = (tb > 0 ? tb : 0) - a.halo;
   for (int i = threadIdx.x; i < span; i += blockDim.x) {
     const int64_t t = lo + i;
     float lp = 0.0f, pv = 0.0f;
     if (t >= 0 && t < F) {
       const float *row = a.raw + (first + t) * a.ld_raw;
-      lp = logf(row[1]);
+      lp = static_cast<float>(log(static_cast<double>(row[1])));
       pv = nccf_to_pov(row[0]);
     }
     s_logp[i] = lp;
@@ -1002,9 +932,10 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
   __syncthreads();
   const snb_pitch_post_opts &o = a.o;
   for (int r = threadIdx.x; r < kPostRows; r += blockDim.x) {
-    const int64_t t = r0 + r;
-    if (t >= F) break;
-    float *out = a.out + (first + t) * a.ld_out;
+    const int64_t to = r0 + r;
+    if (to >= Fo) break;
+    const int64_t t = to < delay ? 0 : to - delay;
+    float *out = a.out + (first_out + to) * a.ld_out;
     int col = 0;
     const float *row = a.raw + (first + t) * a.ld_raw;
     if (o.add_pov_feature) {
@@ -1050,72 +981,93 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
   }
 }
 
-static size_t track_smem(const PitchTables *t);
+// ---------------------------------------------------------------------------
+// launch geometry
+// ---------------------------------------------------------------------------
+constexpr size_t kSmemBudget = 224 * 1024;
 
-static size_t warp_track_smem(const PitchTables *t, int warps) {
-  const WarpSmem L = warp_smem_layout(t->full_len, t->nmeas, t->nstates, t->up_nw_max);
-  return (static_cast<size_t>(warp_shared_floats(t->nstates, t->up_nw_max)) +
-          static_cast<size_t>(warps) * L.total) * 4 + 16;
-}
-
-constexpr size_t kTrackSmemBudget = 224 * 1024;
-constexpr int kTrackWarpsMin = 4;
-
-// most warps (utterances in flight) one CTA can hold
-static int warp_track_capacity(const PitchTables *t) {
-  static const char *env = getenv("SNB_PITCH_WARPS");          // tuning knob: cap the warps per CTA
-  int w = kTrackWarpsMax;
-  if (env && atoi(env) >= kTrackWarpsMin) w = std::min(w, atoi(env) / 4 * 4);
-  while (w >= kTrackWarpsMin && warp_track_smem(t, w) > kTrackSmemBudget) w -= 4;
-  return w;
-}
-
-static bool use_warp_tracker(const PitchTables *t) {
-  static const bool disabled = getenv("SNB_PITCH_CTA") != nullptr;
-  return !disabled && warp_track_capacity(t) >= kTrackWarpsMin && t->nstates <= 32767;
-}
-
-// warp tracker launch shape: one CTA per SM, as many warps per CTA as the batch
-// can feed (multiple of 4, up to the smem capacity); returns the number of
-// concurrently tracked utterances ("slots" of per-utterance scratch)
-static int64_t pitch_slots(const PitchTables *t, int64_t nutts, int *grid_out, int *warps_out) {
+static int sm_count() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
     cudaGetLastError();
     sms = 148;
   }
-  const int cap = warp_track_capacity(t);
-  int64_t w = (std::max<int64_t>(nutts, 1) + sms - 1) / sms;
-  w = (w + 3) / 4 * 4;
-  const int warps = static_cast<int>(std::max<int64_t>(kTrackWarpsMin, std::min<int64_t>(w, cap)));
-  const int64_t want = (std::max<int64_t>(nutts, 1) + warps - 1) / warps;
-  const int grid = static_cast<int>(std::min<int64_t>(want, sms));
+  return sms;
+}
+
+static size_t track_smem(const PitchTables *t, int warps) {
+  return (static_cast<size_t>(track_shared_words(t->nstates)) +
+          static_cast<size_t>(warps) * track_warp_words(t->ns4, t->nstates)) * 4 + 16;
+}
+
+// most warps (utterances in flight) one CTA of the tracker can hold
+static int track_capacity(const PitchTables *t) {
+  static const char *env = getenv("SNB_PITCH_WARPS");          // tuning knob: cap the warps per CTA
+  int w = kTrackWarpsMax;
+  if (env && atoi(env) >= kTrackWarpsMin) w = std::min(w, atoi(env));
+  while (w > 0 && track_smem(t, w) > kSmemBudget) --w;
+  return w;
+}
+
+// Tracker launch shape for `nutts` utterances: one CTA per SM; the number of
+// warps per CTA balances the waves (10 000 utterances on 148 SMs x 28 warps
+// would run 2.4 waves = 3 rounds: 23 warps give 3 full ones).  Returns the
+// number of concurrently tracked utterances ("slots" of backpointer scratch).
+static int64_t track_shape(const PitchTables *t, int64_t nutts, int *grid_out, int *warps_out) {
+  const int sms = sm_count(), cap = track_capacity(t);
+  const int64_t n = std::max<int64_t>(nutts, 1);
+  const int64_t waves = (n + static_cast<int64_t>(sms) * cap - 1) / (static_cast<int64_t>(sms) * cap);
+  int64_t w = (n + waves * sms - 1) / (waves * sms);
+  const int warps = static_cast<int>(std::max<int64_t>(std::min<int64_t>(kTrackWarpsMin, cap), std::min<int64_t>(w, cap)));
+  const int grid = static_cast<int>(std::min<int64_t>((n + warps - 1) / warps, sms));
   if (grid_out) *grid_out = grid;
   if (warps_out) *warps_out = warps;
   return static_cast<int64_t>(grid) * warps;
 }
 
-// persistent CTAs: exactly what is resident at once (a larger grid would run a
-// second, underfilled wave)
-static int pitch_grid(const PitchTables *t, int64_t nutts) {
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
-    cudaGetLastError();
-    sms = 148;
+struct NccfShape { int warps; bool table; size_t smem; };
+static NccfShape nccf_shape(const PitchTables *t) {
+  NccfShape s;
+  const NccfSmem L = nccf_smem_layout(t->full_len, t->nmeas, t->up_nw_max);
+  s.table = static_cast<size_t>(2 * t->up_nw_max) * t->ns_pad * 4 <= 96 * 1024;
+  s.warps = 16;
+  for (;;) {
+    s.smem = static_cast<size_t>(nccf_shared_words(t->nstates, t->ns_pad, t->up_nw_max, s.table)) * 4 +
+             static_cast<size_t>(s.warps) * L.total * 8 + 16;
+    if (s.smem <= 110 * 1024 || s.warps == 1) break;        // two CTAs per SM when possible
+    s.warps >>= 1;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pitch_track_kernel, kPitchThreads,
-                                                    track_smem(t)) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    per_sm = 1;
-  }
-  return static_cast<int>(std::min<int64_t>(nutts, static_cast<int64_t>(sms) * per_sm));
+  return s;
 }
 
-static size_t track_smem(const PitchTables *t) {
-  return static_cast<size_t>(t->full_len + 2 * t->nmeas + 4 * t->nstates + t->nstates * t->up_nw_max) * 4 +
-         static_cast<size_t>(2 * t->nstates) * 4 + 16;
+// Groups of utterances (in sorted order) whose local costs are alive at once.
+// The cost matrix is 4 (ns4 + nm) bytes per frame: a budget of kGroupBytes
+// bounds the scratch whatever the batch; a group is a whole number of tracker
+// waves when it holds several.
+constexpr size_t kGroupBytes = static_cast<size_t>(9) << 30;
+
+static int64_t next_group(const snb_batch *b, const PitchTables *t, int64_t k0, int64_t slots) {
+  const int64_t *gfo = b->down_offsets.data() + 4 * (b->nutts + 1) + b->nutts;
+  const size_t per_frame = static_cast<size_t>(t->ns4 + t->nmeas) * 4;
+  const int64_t budget = static_cast<int64_t>(kGroupBytes / per_frame);
+  int64_t k1 = k0 + 1;
+  while (k1 < b->nutts && gfo[k1 + 1] - gfo[k0] <= budget) ++k1;
+  if (k1 - k0 > slots && k1 < b->nutts) k1 = k0 + (k1 - k0) / slots * slots;
+  return k1;
+}
+
+struct PitchScratch { int64_t group_frames = 0, max_frames = 0; };
+static PitchScratch scratch_shape(const snb_batch *b, const PitchTables *t, int64_t slots) {
+  PitchScratch s;
+  const int64_t *gfo = b->down_offsets.data() + 4 * (b->nutts + 1) + b->nutts;
+  for (int64_t k0 = 0; k0 < b->nutts;) {
+    const int64_t k1 = next_group(b, t, k0, slots);
+    s.group_frames = std::max(s.group_frames, gfo[k1] - gfo[k0]);
+    k0 = k1;
+  }
+  s.max_frames = b->nutts > 0 ? gfo[1] - gfo[0] : 0;     // sorted: the first utterance is the longest
+  return s;
 }
 
 }  // namespace snb
@@ -1127,6 +1079,11 @@ extern "C" int64_t snb_pitch_num_frames(int64_t nsamples, const snb_pitch_opts *
   int32_t first, last;
   lag_range(*po, &first, &last);
   return frames_available(resample_num_out(nsamples, *po, true), *po, last, true);
+}
+
+extern "C" void snb_pitch_num_frames_array(const int64_t *nsamples, int64_t n, const snb_pitch_opts *po,
+                                           int64_t *out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = snb_pitch_num_frames(nsamples[i], po);
 }
 
 extern "C" int snb_pitch_plan_create(const snb_pitch_opts *po, snb_plan **out) {
@@ -1147,25 +1104,33 @@ extern "C" int snb_pitch_plan_create(const snb_pitch_opts *po, snb_plan **out) {
   return SNB_OK;
 }
 
-static int64_t max_frames_of(const snb_batch *b) {
-  int64_t m = 0;
-  for (int64_t u = 0; u < b->nutts; ++u) m = std::max(m, b->frame_offsets[u + 1] - b->frame_offsets[u]);
-  return m;
-}
-
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 extern "C" int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
   if (!plan || plan->kind != 1 || !batch) return -1;
   const PitchTables *t = plan->pitch;
-  const int64_t grid = use_warp_tracker(t) ? pitch_slots(t, batch->nutts, nullptr, nullptr)
-                                           : pitch_grid(t, batch->nutts);
-  const int64_t mf = std::max<int64_t>(1, max_frames_of(batch));
+  const int64_t slots = track_shape(t, batch->nutts, nullptr, nullptr);
+  const PitchScratch s = scratch_shape(batch, t, slots);
+  const int64_t mf = std::max<int64_t>(1, s.max_frames);
   size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4) + 256;   // + utterance queue
-  bytes += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
-  bytes += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
-  bytes += align256(static_cast<size_t>(grid) * mf * 4);
+  bytes += align256(static_cast<size_t>(batch->nutts + 1) * 2 * 4);                 // ballast
+  bytes += align256(static_cast<size_t>(s.group_frames + 1) * t->ns4 * 4);          // local costs
+  bytes += align256(static_cast<size_t>(s.group_frames + 1) * t->nmeas * 4);        // POV NCCF
+  bytes += align256(static_cast<size_t>(slots) * mf * t->nstates * 2);              // backpointers
+  bytes += align256(static_cast<size_t>(slots) * mf * 4);                           // state sequences
   return static_cast<int64_t>(bytes);
+}
+
+template <typename K>
+static int raise_smem(K kernel, std::atomic<size_t> &cur, size_t want) {
+  size_t c = cur.load();
+  while (want > c) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(want));
+    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
+    if (cur.compare_exchange_weak(c, want)) break;
+  }
+  return SNB_OK;
 }
 
 extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, const int16_t *d_pcm,
@@ -1180,27 +1145,36 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   const PitchTables *t = plan->pitch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   batch->note_stream(stream);
-  const bool warp_path = use_warp_tracker(t);
-  int warp_grid = 1, warp_count = kTrackWarpsMin;
-  const int64_t grid = warp_path ? pitch_slots(t, batch->nutts, &warp_grid, &warp_count)
-                                 : pitch_grid(t, batch->nutts);
-  const int64_t mf = std::max<int64_t>(1, max_frames_of(batch));
+  int grid = 1, warps = kTrackWarpsMin;
+  const int64_t slots = track_shape(t, batch->nutts, &grid, &warps);
+  if (warps < 1) return set_error(SNB_ERR_UNSUPPORTED, "pitch options outside the GPU path limits");
+  const PitchScratch sc = scratch_shape(batch, t, slots);
+  const int64_t mf = std::max<int64_t>(1, sc.max_frames);
   unsigned char *ws = static_cast<unsigned char *>(d_workspace);
   float *down = reinterpret_cast<float *>(ws);
   ws += align256(static_cast<size_t>(batch->total_down + 8) * 4);
   unsigned long long *queue = reinterpret_cast<unsigned long long *>(ws);
   ws += 256;
+  float *ballast = reinterpret_cast<float *>(ws);
+  ws += align256(static_cast<size_t>(batch->nutts + 1) * 2 * 4);
+  float *cost = reinterpret_cast<float *>(ws);
+  ws += align256(static_cast<size_t>(sc.group_frames + 1) * t->ns4 * 4);
+  float *pov = reinterpret_cast<float *>(ws);
+  ws += align256(static_cast<size_t>(sc.group_frames + 1) * t->nmeas * 4);
   int16_t *bp = reinterpret_cast<int16_t *>(ws);
-  ws += align256(static_cast<size_t>(grid) * mf * t->nstates * 2);
-  float *pov_raw = reinterpret_cast<float *>(ws);
-  ws += align256(static_cast<size_t>(grid) * mf * t->nmeas * 4);
+  ws += align256(static_cast<size_t>(slots) * mf * t->nstates * 2);
   int32_t *states = reinterpret_cast<int32_t *>(ws);
+
+  const int64_t *d_info = batch->d_down_offsets;
+  const int64_t *d_order = d_info + 4 * (batch->nutts + 1);
+  const int64_t *d_gfo = d_order + batch->nutts;
+  const int64_t *h_gfo = batch->down_offsets.data() + 4 * (batch->nutts + 1) + batch->nutts;
 
   ResampleArgs r;
   r.pcm = d_pcm;
   r.sample_begin = batch->d_sample_begin;
   r.sample_len = batch->d_sample_len;
-  r.info = batch->d_down_offsets;
+  r.info = d_info;
   r.nutts = batch->nutts;
   r.total_down = batch->total_down;
   r.in_unit = t->in_unit; r.out_unit = t->out_unit; r.nw_max = t->down_nw_max;
@@ -1210,58 +1184,59 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
     resample_kernel<<<static_cast<unsigned>((batch->total_down + 255) / 256), 256, 0, stream>>>(r);
     SNB_LAUNCH_CHECK();
   }
-  TrackArgs a;
-  a.down = down;
-  a.info = batch->d_down_offsets;
-  a.frame_offsets = batch->d_frame_offsets;
-  a.nutts = batch->nutts;
-  a.first_lag = t->first_lag; a.nmeas = t->nmeas; a.nstates = t->nstates;
-  a.shift = t->shift; a.basic_len = t->basic_len; a.full_len = t->full_len; a.up_nw_max = t->up_nw_max;
-  a.snip_edges = plan->po.snip_edges;
-  a.preemph = plan->po.preemph_coeff;
-  a.soft_min_f0 = plan->po.soft_min_f0;
-  a.nccf_ballast = plan->po.nccf_ballast;
-  a.lags = t->d_lags; a.pen = t->d_pen; a.up_w = t->d_up_w;
-  a.up_first = t->d_up_first; a.up_nw = t->d_up_nw;
-  a.bp = bp; a.pov_raw = pov_raw; a.states = states;
-  a.max_frames = mf;
-  a.out = d_out; a.ld_out = ld_out;
-  a.queue = queue;
-  if (warp_path) {
-    const size_t wsmem = warp_track_smem(t, warp_count);
-    static std::atomic<size_t> wcur{48 * 1024};
-    size_t c = wcur.load();
-    while (wsmem > c) {
-      cudaError_t e = cudaFuncSetAttribute(pitch_track_warp_kernel<10>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem));
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(pitch_track_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(wsmem));
-      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
-      if (wcur.compare_exchange_weak(c, wsmem)) break;
-    }
-    cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
-    if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch queue: %s", cudaGetErrorString(e));
-    if (t->up_nw_max == 10)     // Kaldi's default resampling options
-      pitch_track_warp_kernel<10><<<static_cast<unsigned>(warp_grid), warp_count * 32, wsmem, stream>>>(a);
-    else
-      pitch_track_warp_kernel<0><<<static_cast<unsigned>(warp_grid), warp_count * 32, wsmem, stream>>>(a);
-    SNB_LAUNCH_CHECK();
-    return SNB_OK;
-  }
-  const size_t smem = track_smem(t);
-  {
-    static std::atomic<size_t> cur{48 * 1024};
-    size_t c = cur.load();
-    while (smem > c) {
-      cudaError_t e = cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
-      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch smem: %s", cudaGetErrorString(e));
-      if (cur.compare_exchange_weak(c, smem)) break;
-    }
-  }
-  pitch_track_kernel<<<static_cast<unsigned>(grid), kPitchThreads, smem, stream>>>(a);
+  BallastArgs ba;
+  ba.down = down; ba.info = d_info; ba.basic_len = t->basic_len;
+  ba.nccf_ballast = plan->po.nccf_ballast; ba.ballast = ballast;
+  pitch_ballast_kernel<<<static_cast<unsigned>(batch->nutts), 256, 0, stream>>>(ba);
   SNB_LAUNCH_CHECK();
+
+  const NccfShape nshape = nccf_shape(t);
+  static std::atomic<size_t> nccf_cur{48 * 1024}, track_cur{48 * 1024};
+  int rc = raise_smem(pitch_nccf_kernel, nccf_cur, nshape.smem);
+  if (rc != SNB_OK) return rc;
+  const size_t tsmem = track_smem(t, warps);
+  rc = raise_smem(pitch_viterbi_kernel, track_cur, tsmem);
+  if (rc != SNB_OK) return rc;
+  const int sms = sm_count();
+
+  for (int64_t k0 = 0; k0 < batch->nutts;) {
+    const int64_t k1 = next_group(batch, t, k0, slots);
+    const int64_t q0 = h_gfo[k0], q1 = h_gfo[k1];
+    if (q1 > q0) {
+      NccfArgs n;
+      n.down = down; n.info = d_info; n.order = d_order; n.gfo = d_gfo; n.ballast = ballast;
+      n.k0 = k0; n.k1 = k1; n.q0 = q0; n.q1 = q1;
+      n.first_lag = t->first_lag; n.nmeas = t->nmeas; n.nstates = t->nstates; n.ns4 = t->ns4;
+      n.shift = t->shift; n.basic_len = t->basic_len; n.full_len = t->full_len;
+      n.nw = t->up_nw_max; n.ns_pad = t->ns_pad;
+      n.snip_edges = plan->po.snip_edges; n.table_in_smem = nshape.table ? 1 : 0;
+      n.preemph = plan->po.preemph_coeff; n.soft_min_f0 = plan->po.soft_min_f0;
+      n.lags = t->d_lags; n.up_w_t = t->d_up_w_t; n.up_first = t->d_up_first;
+      n.cost = cost; n.pov = pov;
+      const int64_t ntasks = (q1 - q0 + kNccfTask - 1) / kNccfTask;
+      const int64_t want = (ntasks + nshape.warps - 1) / nshape.warps;
+      const unsigned ngrid = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * 2));
+      pitch_nccf_kernel<<<ngrid, nshape.warps * 32, nshape.smem, stream>>>(n);
+      SNB_LAUNCH_CHECK();
+
+      TrackArgs a;
+      a.cost = cost; a.pov = pov;
+      a.order = d_order; a.gfo = d_gfo; a.frame_offsets = batch->d_frame_offsets;
+      a.k0 = k0; a.k1 = k1; a.q0 = q0;
+      a.nstates = t->nstates; a.ns4 = t->ns4; a.nmeas = t->nmeas; a.nw = t->up_nw_max; a.ns_pad = t->ns_pad;
+      a.lags = t->d_lags; a.pen = t->d_pen; a.up_w_t = t->d_up_w_t; a.up_first = t->d_up_first;
+      a.bp = bp; a.states = states; a.max_frames = mf;
+      a.out = d_out; a.ld_out = ld_out;
+      a.queue = queue;
+      cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
+      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "pitch queue: %s", cudaGetErrorString(e));
+      const int64_t gutts = k1 - k0;
+      const int ggrid = static_cast<int>(std::min<int64_t>((gutts + warps - 1) / warps, grid));
+      pitch_viterbi_kernel<<<static_cast<unsigned>(ggrid), warps * 32, tsmem, stream>>>(a);
+      SNB_LAUNCH_CHECK();
+    }
+    k0 = k1;
+  }
   return SNB_OK;
 }
 
@@ -1271,14 +1246,15 @@ extern "C" int32_t snb_process_pitch_dim(const snb_pitch_post_opts *o) {
 }
 
 extern "C" int snb_process_pitch(const snb_pitch_post_opts *o, const float *d_raw, int64_t ld_raw,
-                                 const int64_t *d_frame_offsets, int64_t nutts, int64_t total_frames,
-                                 int64_t max_frames, uint64_t seed, float *d_out, int64_t ld_out,
-                                 void *stream) {
+                                 const int64_t *d_frame_offsets, const int64_t *d_out_frame_offsets,
+                                 int64_t nutts, int64_t total_frames, int64_t max_frames, uint64_t seed,
+                                 float *d_out, int64_t ld_out, void *stream) {
   if (!o) return set_error(SNB_ERR_VALUE, "null options");
   const int dim = snb_process_pitch_dim(o);
   if (dim == 0)
     return set_error(SNB_ERR_VALUE, "at least one of the pitch features must be enabled");
-  if (o->delay != 0) return set_error(SNB_ERR_UNSUPPORTED, "delay != 0 is not supported on the GPU path");
+  // Kaldi asserts frame - delay < NumFramesReady() = F + delay: a negative delay aborts there
+  if (o->delay < 0) return set_error(SNB_ERR_OPTION, "delay must be >= 0");
   if (total_frames == 0 || nutts == 0) return SNB_OK;
   if (!d_raw || !d_out || ld_raw < 2 || ld_out < dim) return set_error(SNB_ERR_VALUE, "bad argument");
   if (o->normalization_left_context < 0 || o->normalization_right_context < 0 || o->delta_window <= 0)
@@ -1287,22 +1263,17 @@ extern "C" int snb_process_pitch(const snb_pitch_post_opts *o, const float *d_ra
   a.o = *o;
   a.raw = d_raw; a.ld_raw = ld_raw;
   a.frame_offsets = d_frame_offsets;
+  a.out_offsets = d_out_frame_offsets;
   a.seed = seed;
   a.out = d_out; a.ld_out = ld_out;
   a.halo = std::max(std::max(o->normalization_left_context, o->normalization_right_context), o->delta_window);
   const size_t smem = static_cast<size_t>(kPostRows + 2 * a.halo) * 2 * 4;
   if (smem > 200 * 1024) return set_error(SNB_ERR_UNSUPPORTED, "normalisation context too large");
-  {
-    static std::atomic<size_t> cur{48 * 1024};
-    size_t c = cur.load();
-    while (smem > c) {
-      cudaError_t e = cudaFuncSetAttribute(process_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
-      if (e != cudaSuccess) return set_error(SNB_ERR_CUDA, "post smem: %s", cudaGetErrorString(e));
-      if (cur.compare_exchange_weak(c, smem)) break;
-    }
-  }
-  const unsigned chunks = static_cast<unsigned>((std::max<int64_t>(max_frames, 1) + kPostRows - 1) / kPostRows);
+  static std::atomic<size_t> cur{48 * 1024};
+  int rc = raise_smem(process_pitch_kernel, cur, smem);
+  if (rc != SNB_OK) return rc;
+  const unsigned chunks =
+      static_cast<unsigned>((std::max<int64_t>(max_frames, 1) + o->delay + kPostRows - 1) / kPostRows);
   if (chunks > 65535) return set_error(SNB_ERR_UNSUPPORTED, "utterance too long for process_pitch");
   process_pitch_kernel<<<dim3(static_cast<unsigned>(nutts), chunks), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
   SNB_LAUNCH_CHECK();

@@ -357,15 +357,28 @@ def f64_to_f32(x):
     return out
 
 
-def process_pitch(post_opts, raw, layout, seed=0, out=None):
+def process_pitch(post_opts, raw, layout, seed=0, out=None, out_layout=None):
+    """Pitch post-processing of raw [total, 2] (NCCF, pitch) rows
+
+    With ``delay = d > 0`` an utterance of F > 0 frames gives F + d rows (row
+    t holds the features of frame max(0, t - d), like Kaldi's ProcessPitch):
+    the rows of utterance u then start at ``frame_offsets[u] + u * d`` and the
+    output has ``total + nutts * d`` rows.  With `out_layout` (a RowLayout)
+    the rows of utterance u go to its rows of `out` instead, trimmed to their
+    number (pasting next to features that are a frame or two shorter).
+    """
     torch = require_cuda()
     L = _lib.lib()
     dim = int(L.snb_process_pitch_dim(_lib.ref(post_opts)))
+    delay = max(int(post_opts.delay), 0)
     if out is None:
-        out = torch.empty((raw.shape[0], max(dim, 1)), dtype=torch.float32,
+        rows = (out_layout.total if out_layout is not None
+                else raw.shape[0] + delay * layout.nutts)
+        out = torch.zeros((rows, max(dim, 1)), dtype=torch.float32,
                           device='cuda')
     _lib.check(L.snb_process_pitch(
         _lib.ref(post_opts), _ptr(raw), raw.stride(0), layout.ptr,
+        out_layout.ptr if out_layout is not None else None,
         layout.nutts, layout.total, layout.max_frames,
         ctypes.c_uint64(int(seed) & (2**64 - 1)), _ptr(out), out.stride(0),
         _stream_ptr()))

@@ -51,6 +51,12 @@ class FusedPipeline:
         self.pitch = pitch
         if vad is not None and energy is None:
             raise ValueError('vad needs an energy processor')
+        if pitch is not None and pitch[1].delay != 0:
+            # Kaldi returns nframes + delay rows: the reference fails on the
+            # mismatch with the frame times (pitch_kaldi.py:535-540)
+            raise ValueError(
+                'pitch postprocessing with delay != 0 changes the number of '
+                'frames: mismatch between data and times')
         self.base_dim = processor.ndims
         order = delta.order if delta is not None else 0
         self.feat_dim = self.base_dim * (order + 1)

@@ -237,7 +237,11 @@ class KaldiPitchPostProcessor(FeaturesPostProcessor):
         """Post-processes the raw pitch [nframes, 2] -> [nframes, 1..4]
 
         ValueError if `raw_pitch` has not exactly two columns or if all the
-        ``add_*`` options are False.
+        ``add_*`` options are False.  With ``delay != 0`` Kaldi returns
+        ``nframes + delay`` rows, which the reference pairs with the
+        ``nframes`` input times (pitch_kaldi.py:535-540): the Features
+        constructor rejects that there and here (ValueError).  The delayed
+        rows themselves are available from ``engine.process_pitch``.
         """
         self._validate(raw_pitch.shape[1])
         x = engine.from_host(raw_pitch.data, np.float32)
