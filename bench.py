@@ -3,30 +3,47 @@
 
     python bench.py --gpus N --steps K --warmup W        (torchrun for N > 1)
     python bench.py --impl reference ...                  (CPU arm)
+    python bench.py --config {1,2,3,4} ...                (BASELINE.json configs[k])
 
-Workload (config.workload): BASELINE.json configs[2], the MFCC configuration
-the metric is quoted on that fits one GPU -- MfccProcessor (reference
-defaults, dither=1.0) + per-utterance CMVN + DeltaPostProcessor(order=2) on
-10 000 synthetic 16 kHz 10 s utterances PER GPU (weak scaling: utterances are
-independent, each rank owns its shard, no data-path collective).  One "step"
-is one pass of the whole pipeline over the rank's batch.
+Default workload (config.workload): BASELINE.json configs[2], the MFCC
+configuration the metric is quoted on that fits one GPU -- MfccProcessor
+(reference defaults, dither=1.0) + per-utterance CMVN + DeltaPostProcessor
+(order=2) on 10 000 synthetic 16 kHz 10 s utterances PER GPU (weak scaling:
+utterances are independent, each rank owns its shard).  One "step" is one pass
+of the whole pipeline over the rank's batch.  configs[3] (PLP + Kaldi pitch,
+50 000 utterances over 8 GPUs = 6 250 per GPU) and configs[4] (filterbank +
+pitch + delta + CMVN by speaker with VAD, 100 h = 36 000 utterances over 8
+GPUs = 4 500 per GPU) are the two 8-GPU configurations of BASELINE.json.
 
 * value      : frames/s with the int16 PCM already resident in HBM (CUDA
-               events around K steps, max over ranks, whole-job aggregate)
+               events around K steps, max over ranks, whole-job aggregate).
+               For N > 1 the COLLECTION is inside the step: the rank's batch
+               is cut in chunks and the rows of chunk k are all-gathered to
+               every rank (NCCL over NVLink, own stream) while chunk k + 1 is
+               computed; the step ends when every rank holds every row.
 * e2e        : same metric through the host API with pinned HOST buffers:
                H2D of the PCM and D2H of the features inside the timed region
+               (FusedPipeline.run_host = shennong_b200.stream.StreamRunner)
+* e2e_api    : the reference-facing calls on WAV files:
+               MfccProcessor().process_all(Utterances) and
+               pipeline.extract_features(config, Utterances) (sharded over the
+               ranks, rows gathered to every rank)
 * roofline   : dominant kernel (fused_features_512_kernel): algorithmic
-               bytes/launch (372 B/frame: 320 B int16 PCM read + 13 floats
-               written) / its mean duration, vs the measured HBM peak
+               bytes/launch (320 B int16 PCM read + 4 B x base columns
+               written per frame) / its mean duration, vs the measured HBM peak
 * cpu_baseline: the C oracle port of the reference path (Kaldi restatement),
                OpenMP over utterances on all host cores, bounded sample
+* check      : rank 0 compares rows of every rank (dither 0) with the oracle
 """
 
 import argparse
+import concurrent.futures
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -38,23 +55,15 @@ sys.path.insert(0, ROOT)
 SAMPLE_RATE = 16000
 UTT_SAMPLES = 160000            # 10 s
 FRAMES_PER_UTT = 998
-BYTES_PER_FRAME_KERNEL = 320 + 4 * 13     # PCM read once + 13 cepstra written
+UTTS_PER_SPEAKER = 100
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_features_512_kernel
-# launch over 9.98e6 frames (ncu capture of `bench.py --steps 2 --warmup 2`,
-# profiles/r01_final_ncu_traffic_fused_features_512.csv): 3 242 790 912 +
-# 512 223 488 B = 376.3 B/frame, i.e. 1.011 x the algorithmic bytes (the
-# extra 2 B/frame is the 32-byte tile descriptor per 16 frames)
+# launch over 9.98e6 frames of MFCC-13 (ncu capture of `bench.py --steps 2
+# --warmup 2`, profiles/r01_final_ncu_traffic_fused_features_512.csv):
+# 3 242 790 912 + 512 223 488 B = 376.3 B/frame, i.e. 1.011 x the algorithmic
+# bytes (the extra is the 32-byte tile descriptor per 16 frames)
 NCU_TRAFFIC_BYTES_PER_FRAME = (3242790912 + 512223488) / 9980000.0
 TRAFFIC_SOURCE = ('ncu capture of this launch shape, '
                   'profiles/r01_final_ncu_traffic_fused_features_512.csv')
-# what actually bounds the dominant kernel (ncu --set full of the same kernel on
-# 2 000 utterances, profiles/r01_final_ncu_fused_features_512_dither*.txt)
-NCU_LIMITS = {
-    'source': 'profiles/r01_final_ncu_fused_features_512_dither1.0.txt',
-    'issue_slots_busy_pct': 72.9, 'smem_data_pipe_busy_pct': 64.0,
-    'warp_instructions_per_frame': 936, 'smem_wavefronts_per_frame': 215,
-    'dram_throughput_pct': 4.0}
-BYTES_PER_FRAME_PIPELINE = 320 + 4 * 39   # + delta/cmvn output
 FLOPS_PER_FRAME = 17000
 
 
@@ -64,14 +73,70 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--utts', type=int, default=10000,
-                    help='utterances per GPU')
+    ap.add_argument('--config', type=int, default=2, choices=[1, 2, 3, 4],
+                    help='index in BASELINE.json configs')
+    ap.add_argument('--utts', type=int, default=0,
+                    help='utterances per GPU (default: the configuration\'s)')
     ap.add_argument('--dither', type=float, default=1.0)
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-api', action='store_true')
+    ap.add_argument('--api-utts', type=int, default=2000)
     ap.add_argument('--chunk-utts', type=int, default=512,
                     help='utterances per chunk of the host pipeline (e2e)')
+    ap.add_argument('--gather-chunks', type=int, default=8,
+                    help='chunks of the device-resident step for N > 1')
+    ap.add_argument('--gather', default='nccl', choices=['nccl', 'none'])
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# configurations (BASELINE.json configs[k])
+# --------------------------------------------------------------------------
+def make_config(index, dither):
+    """(FusedPipeline, description dict) for BASELINE.json configs[index]"""
+    from shennong_b200.fused import FusedPipeline
+    from shennong_b200.postprocessor import (
+        DeltaPostProcessor, VadPostProcessor)
+    from shennong_b200.processor import (
+        EnergyProcessor, FilterbankProcessor, KaldiPitchPostProcessor,
+        KaldiPitchProcessor, MfccProcessor, PlpProcessor)
+    if index == 1:
+        pipe = FusedPipeline(FilterbankProcessor(num_bins=40, dither=dither))
+        info = dict(utts=1000, oracle=('filterbank', dict(num_bins=40)),
+                    metric='filterbank-40 frames/sec',
+                    workload='BASELINE configs[1]: FilterbankProcessor 40-mel')
+    elif index == 2:
+        pipe = FusedPipeline(
+            MfccProcessor(dither=dither),
+            delta=DeltaPostProcessor(order=2, window=2), cmvn='utterance',
+            norm_vars=True)
+        info = dict(utts=10000, oracle=('mfcc', {}),
+                    metric='MFCC frames/sec',
+                    workload='BASELINE configs[2]: MfccProcessor (13 ceps, '
+                    '23 mel, reference defaults) + CMVN per utterance '
+                    '(norm_vars) + DeltaPostProcessor(order=2, window=2)')
+    elif index == 3:
+        pipe = FusedPipeline(
+            PlpProcessor(dither=dither),
+            pitch=(KaldiPitchProcessor(), KaldiPitchPostProcessor()))
+        info = dict(utts=6250, oracle=('plp', {}),
+                    metric='PLP + Kaldi pitch frames/sec',
+                    workload='BASELINE configs[3]: PlpProcessor + '
+                    'KaldiPitchProcessor (+ post-processing) pipeline, '
+                    '50 000 utterances over 8 GPUs')
+    else:
+        pipe = FusedPipeline(
+            FilterbankProcessor(dither=dither),
+            delta=DeltaPostProcessor(order=2, window=2), cmvn='speaker',
+            vad=VadPostProcessor(), energy=EnergyProcessor(),
+            pitch=(KaldiPitchProcessor(), KaldiPitchPostProcessor()))
+        info = dict(utts=4500, oracle=('filterbank', {}),
+                    metric='full pipeline frames/sec',
+                    workload='BASELINE configs[4]: speech-features full '
+                    'pipeline (filterbank + Kaldi pitch + delta + CMVN by '
+                    'speaker with VAD), 100 h = 36 000 utterances over 8 GPUs')
+    return pipe, info
 
 
 def measured_peaks():
@@ -83,10 +148,39 @@ def measured_peaks():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+# --------------------------------------------------------------------------
+# synthetic corpus
+# --------------------------------------------------------------------------
+def synth_utterance(index, nsamples=UTT_SAMPLES):
+    """Utterance `index` of the synthetic corpus on the host: 5-harmonic tone
+    (f0 ~ U(80, 300) Hz, amplitude 3000/h) + N(0, 500^2) noise, clipped to
+    int16; seeded per utterance (same generator as tests/conftest.py)"""
+    rng = np.random.default_rng(20260925 + index)
+    f0 = rng.uniform(80, 300)
+    phases = rng.uniform(0, 2 * np.pi, 5)
+    t = np.arange(nsamples) / SAMPLE_RATE
+    x = sum(3000.0 / h * np.sin(2 * np.pi * h * f0 * t + phases[h - 1])
+            for h in range(1, 6))
+    x = x + 500.0 * rng.standard_normal(nsamples)
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+def synth_host(first, count):
+    """Utterances [first, first + count) of the corpus, generated on all host
+    cores, as one int16 array [count * UTT_SAMPLES]"""
+    out = np.empty(count * UTT_SAMPLES, dtype=np.int16)
+    workers = min(os.cpu_count() or 1, 32, max(count, 1))
+
+    def fill(u):
+        out[u * UTT_SAMPLES:(u + 1) * UTT_SAMPLES] = synth_utterance(first + u)
+    with concurrent.futures.ThreadPoolExecutor(workers) as pool:
+        list(pool.map(fill, range(count)))
+    return out
+
+
 def synth_pcm_device(nutts, rank, torch):
-    """Synthetic corpus of BASELINE.md section 3 generated on the device:
-    5-harmonic tone (f0 ~ U(80, 300) Hz, amplitude 3000/h) + N(0, 500^2)
-    noise, clipped to int16; seeded by (20260925, rank)."""
+    """The same distribution generated on the device (bulk of the corpus):
+    seeded by (20260925, rank)"""
     gen = torch.Generator(device='cuda')
     gen.manual_seed(20260925 + 7919 * rank)
     out = torch.empty((nutts, UTT_SAMPLES), dtype=torch.int16, device='cuda')
@@ -162,40 +256,165 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def oracle_kwargs(dither):
-    return dict(dither=dither)
-
-
-def cpu_baseline(pcm_host, nutts_avail, dither, budget_s=12.0):
-    """Times the CPU oracle port (mfcc + cmvn + delta, OpenMP over utterances)
-    on a bounded sample of the same workload"""
+# --------------------------------------------------------------------------
+# CPU arm: the oracle port of the same pipeline
+# --------------------------------------------------------------------------
+def oracle_pass(index, pcm_host, n, dither, cores):
+    """One pass of the configuration's pipeline over the first n utterances
+    on the CPU oracle; returns (seconds, frames)"""
     import oracle
-    cores = os.cpu_count() or 1
-    offs = np.arange(nutts_avail + 1, dtype=np.int64) * UTT_SAMPLES
+    offs = np.arange(n + 1, dtype=np.int64) * UTT_SAMPLES
+    pcm = pcm_host[:n * UTT_SAMPLES]
+    t0 = time.perf_counter()
+    if index == 2:
+        _, fofs = oracle.pipeline_batch(
+            'mfcc', pcm, offs, cmvn=True, norm_vars=True, delta_order=2,
+            delta_window=2, nthreads=cores, dither=dither)
+        frames = int(fofs[-1])
+    elif index == 1:
+        _, fofs = oracle.features_batch(
+            'filterbank', pcm, offs, nthreads=cores, dither=dither,
+            num_bins=40)
+        frames = int(fofs[-1])
+    else:
+        frames = oracle_pass_pitch(index, pcm, n, dither, cores)
+    return time.perf_counter() - t0, frames
 
-    def run(n):
-        t0 = time.perf_counter()
-        out, fofs = oracle.pipeline_batch(
-            'mfcc', pcm_host[:n * UTT_SAMPLES], offs[:n + 1], cmvn=True,
-            norm_vars=True, delta_order=2, delta_window=2, nthreads=cores,
-            dither=dither)
-        return time.perf_counter() - t0, int(fofs[-1])
+
+def oracle_pass_pitch(index, pcm, n, dither, cores):
+    """configs[3] / configs[4] on the oracle: the batch entry points for the
+    spectral features, a thread pool over utterances for pitch (the C calls
+    release the GIL) and the post-processors"""
+    import oracle
+    offs = np.arange(n + 1, dtype=np.int64) * UTT_SAMPLES
+    kind = 'plp' if index == 3 else 'filterbank'
+    base, fofs = oracle.features_batch(
+        kind, pcm, offs, nthreads=cores, dither=dither)
+
+    def one(u):
+        sig = pcm[u * UTT_SAMPLES:(u + 1) * UTT_SAMPLES]
+        post = oracle.process_pitch(oracle.pitch(sig))
+        feats = base[fofs[u]:fofs[u + 1]]
+        if index == 4:
+            energy = oracle.features('energy', sig, dither=dither)
+            weights = oracle.vad(energy.astype(np.float32).reshape(-1, 1))
+            return feats, post, oracle.cmvn_accumulate(
+                feats, weights.reshape(-1).astype(np.float32))
+        return feats, post, None
+    with concurrent.futures.ThreadPoolExecutor(cores) as pool:
+        parts = list(pool.map(one, range(n)))
+    if index == 4:
+        for s0 in range(0, n, UTTS_PER_SPEAKER):
+            group = parts[s0:s0 + UTTS_PER_SPEAKER]
+            stats = sum(p[2] for p in group)
+            for feats, post, _ in group:
+                np.hstack((oracle.deltas(oracle.cmvn_apply(feats, stats)),
+                           post[:feats.shape[0]]))
+    return int(fofs[-1])
+
+
+def cpu_baseline(index, pcm_host, nutts_avail, dither, budget_s=12.0):
+    """Times the CPU oracle port on a bounded sample of the same workload:
+    about `budget_s` seconds of passes over the first n utterances"""
+    cores = os.cpu_count() or 1
     probe = min(nutts_avail, max(cores, 8))
-    dt, frames = run(probe)
+    dt, frames = oracle_pass(index, pcm_host, probe, dither, cores)
     rate = frames / dt
     n = int(min(nutts_avail, max(probe, rate * budget_s / FRAMES_PER_UTT)))
-    # passes over the sample until about budget_s of CPU work has been timed
     reps = int(max(1, min(64, round(budget_s * rate / (n * FRAMES_PER_UTT)))))
-    dt, frames = 0.0, 0
+    times, frames = [], 0
     for _ in range(reps):
-        d, f = run(n)
-        dt += d
+        d, f = oracle_pass(index, pcm_host, n, dither, cores)
+        times.append(d)
         frames += f
-    return {'value': frames / dt, 'unit': 'frames/s', 'cores': cores,
+    total = float(sum(times))
+    return {'value': frames / total, 'unit': 'frames/s', 'cores': cores,
             'kind': 'port',
-            'sample': f'{reps} pass(es) over {n} of the synthetic 10 s '
-                      f'utterances ({frames} frames) in {dt:.2f} s, C oracle, '
-                      f'OpenMP over utterances'}, n, dt
+            'sample': f'{reps} pass(es) over the first {n} utterances of the '
+                      f'synthetic corpus ({frames} frames) in {total:.2f} s, '
+                      f'C oracle, OpenMP / threads over utterances'}, n, times
+
+
+def reference_arm(args, config):
+    """--impl reference: the reference's own CPU implementation cannot be
+    imported (pykaldi is absent): the arm times the
+    oracle port on all host cores.  Nothing of libsnb is loaded."""
+    import oracle
+    oracle.build()
+    nutts = min(args.utts or 2048, 2048)
+    pcm = synth_host(0, nutts)
+    cores = os.cpu_count() or 1
+    # one step = one pass over n utterances, n sized for about 8 s
+    probe = min(nutts, max(cores, 8))
+    dt, frames = oracle_pass(args.config, pcm, probe, args.dither, cores)
+    n = int(min(nutts, max(probe, frames / dt * 8.0 / FRAMES_PER_UTT)))
+    times, frames = [], 0
+    for step in range(args.warmup + args.steps):
+        d, f = oracle_pass(args.config, pcm, n, args.dither, cores)
+        if step >= args.warmup:
+            times.append(d)
+            frames += f
+    value = frames / float(sum(times))
+    config = dict(config, cpu_sample_utterances=n,
+                  sharding='rank 0 only, all host cores')
+    base = {'value': value, 'unit': 'frames/s', 'cores': cores,
+            'kind': 'port',
+            'sample': f'each step = one pass over the first {n} utterances '
+                      f'of the synthetic corpus ({n * FRAMES_PER_UTT} '
+                      f'frames), C oracle, OpenMP / threads over utterances'}
+    return {
+        'impl': 'reference', 'metric': config['metric'], 'value': value,
+        'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': float(np.mean(times) * 1e3),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': config,
+        'cpu_baseline': base,
+        'e2e': {'value': value, 'unit': 'frames/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+# --------------------------------------------------------------------------
+# host placement
+# --------------------------------------------------------------------------
+def bind_to_gpu_node(local_rank, world, torch):
+    """Runs this rank (and first-touches its pinned buffers) on the CPUs of
+    its GPU's NUMA node, split between the ranks that share the node"""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        domain = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist' % (
+            domain, bus, dev)
+        cpus = []
+        for part in open(path).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        sharing = [r for r in range(world) if _cpulist(r, torch) == cpus]
+        k, m = sharing.index(local_rank), len(sharing)
+        mine = allowed[k * len(allowed) // m:(k + 1) * len(allowed) // m]
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return {'cpus': len(mine), 'node_cpus': len(allowed),
+                'ranks_on_node': m}
+    except Exception:
+        return None
+
+
+def _cpulist(rank, torch):
+    try:
+        p = torch.cuda.get_device_properties(rank)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist' % (
+            p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpus = []
+        for part in open(path).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        return cpus
+    except Exception:
+        return None
 
 
 def main():
@@ -203,110 +422,107 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        _, info = config_info(args)
+        print(json.dumps(reference_arm(args, info)))
+        return
+
     import __graft_entry__
     if rank == 0:
         __graft_entry__.build()
-
-    config = {
-        'workload': ('BASELINE configs[2]: MfccProcessor (13 ceps, 23 mel, '
-                     'reference defaults) + CMVN per utterance (norm_vars) + '
-                     'DeltaPostProcessor(order=2, window=2) on '
-                     f'{args.utts} synthetic 16 kHz 10 s utterances per GPU'),
-        'utterances_per_gpu': args.utts, 'frames_per_utterance': FRAMES_PER_UTT,
-        'dither': args.dither, 'sharding': f'utterances x{world} (no collective)',
-        'l2': 'inputs (3.2 GB/GPU) larger than the 126 MB L2',
-    }
-
-    if args.impl == 'reference':
-        # the reference's own CPU implementation cannot be imported (pykaldi is
-        # absent): the arm times the oracle port on all host cores
-        if rank != 0:
-            return
-        import torch
-        nutts = min(args.utts, 2048)
-        rng = np.random.default_rng(20260925)
-        # same distribution as the GPU corpus, generated on the host
-        t = np.arange(UTT_SAMPLES, dtype=np.float32) / SAMPLE_RATE
-        pcm = np.empty(nutts * UTT_SAMPLES, dtype=np.int16)
-        for u in range(nutts):
-            f0 = rng.uniform(80, 300)
-            x = 500.0 * rng.standard_normal(UTT_SAMPLES, dtype=np.float32)
-            for h in range(1, 6):
-                x += (3000.0 / h) * np.sin(
-                    2 * np.pi * h * f0 * t + rng.uniform(0, 2 * np.pi))
-            pcm[u * UTT_SAMPLES:(u + 1) * UTT_SAMPLES] = np.clip(
-                np.round(x), -32768, 32767)
-        values = []
-        for step in range(args.warmup + args.steps):
-            base, n, dt = cpu_baseline(pcm, nutts, args.dither, budget_s=8.0)
-            if step >= args.warmup:
-                values.append((base, n, dt))
-        value = float(np.mean([b['value'] for b, _, _ in values]))
-        base = values[-1][0]
-        base['value'] = value
-        print(json.dumps({
-            'impl': 'reference', 'metric': 'MFCC frames/sec', 'value': value,
-            'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup,
-            'ms_per_step': float(np.mean([dt for _, _, dt in values]) * 1e3),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': config,
-            'cpu_baseline': base,
-            'e2e': {'value': value, 'unit': 'frames/s',
-                    'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
-        return
-
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')
         dist.init_process_group(
             'nccl', device_id=torch.device('cuda', local_rank))
-    from shennong_b200 import _lib, engine
-    from shennong_b200.fused import FusedPipeline
-    from shennong_b200.postprocessor import DeltaPostProcessor
-    from shennong_b200.processor import MfccProcessor
+    placement = bind_to_gpu_node(local_rank, world, torch)
+    from shennong_b200 import _lib, engine, stream
 
-    proc = MfccProcessor(dither=args.dither)
-    pipe = FusedPipeline(proc, delta=DeltaPostProcessor(order=2, window=2),
-                         cmvn='utterance', norm_vars=True)
+    pipe, info = make_config(args.config, args.dither)
+    nutts = args.utts or info['utts']
+    config = describe(args, info, nutts, world)
     plans = pipe._plans()
-    nutts = args.utts
-    pcm_dev = synth_pcm_device(nutts, rank, torch)
-    pad = torch.zeros(64, dtype=torch.int16, device='cuda')
-    pcm_dev = torch.cat([pcm_dev, pad])
-    starts = np.arange(nutts, dtype=np.int64) * UTT_SAMPLES
-    lengths = np.full(nutts, UTT_SAMPLES, dtype=np.int64)
-    packed = engine.PackedAudio.from_packed(None, starts, lengths, dev=pcm_dev)
-    batch = engine.Batch(plans['feat'], packed)
-    layout = engine.RowLayout(batch=batch)
-    total_frames = batch.total_frames
-    base = torch.empty((total_frames, 13), dtype=torch.float32, device='cuda')
-    out = torch.empty((total_frames, 39), dtype=torch.float32, device='cuda')
     L = _lib.lib()
-
-    ev_feat = [(torch.cuda.Event(enable_timing=True),
-                torch.cuda.Event(enable_timing=True))
-               for _ in range(args.steps)]
-
-    def step(i=None, seed=1):
-        if i is not None:
-            ev_feat[i][0].record()
-        engine.compute_features(plans['feat'], batch, seed=seed, out=base)
-        if i is not None:
-            ev_feat[i][1].record()
-        stats = engine.cmvn_accumulate(base, layout)
-        norm = engine.cmvn_norm(stats, True, False)
-        engine.deltas(base, layout, 2, 2, norm=norm, out=out)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- corpus: device-generated, the first utterances host-generated -----
+    # (those are the ones the CPU arms and the parity check read)
+    nhost = min(nutts, 2048 if (rank == 0 and not args.no_cpu) else 8)
+    host_head = synth_host(rank * nutts, nhost)
+    pcm_dev = torch.cat([synth_pcm_device(nutts, rank, torch),
+                         torch.zeros(64, dtype=torch.int16, device='cuda')])
+    pcm_dev[:nhost * UTT_SAMPLES].copy_(torch.from_numpy(host_head))
+    starts = np.arange(nutts, dtype=np.int64) * UTT_SAMPLES
+    lengths = np.full(nutts, UTT_SAMPLES, dtype=np.int64)
+    speakers = ['spk%05d' % (u // UTTS_PER_SPEAKER) for u in range(nutts)]
+
+    # ---- chunks of the device-resident step (one chunk when N = 1) ---------
+    nchunks = 1
+    if world > 1 and args.gather != 'none':
+        nchunks = max(1, min(args.gather_chunks, nutts // UTTS_PER_SPEAKER))
+    per = -(-nutts // nchunks)
+    per = -(-per // UTTS_PER_SPEAKER) * UTTS_PER_SPEAKER     # whole speakers
+    bounds = [(b, min(b + per, nutts)) for b in range(0, nutts, per)]
+    chunks = []
+    total_frames = 0
+    out = None
+    for b, e in bounds:
+        packed = engine.PackedAudio.from_packed(
+            None, starts[b:e] - starts[b], lengths[b:e],
+            dev=pcm_dev[int(starts[b]):])
+        batches = pipe.make_batches(plans, packed)
+        rows = batches['feat'].total_frames
+        chunks.append(dict(packed=packed, batches=batches, rows=rows,
+                           row0=total_frames, spk=speakers[b:e]))
+        total_frames += rows
+    out = torch.empty((total_frames, pipe.out_dim), dtype=torch.float32,
+                      device='cuda')
+    base = (None if pipe.simple else torch.empty(
+        (total_frames, pipe.base_dim), dtype=torch.float32, device='cuda'))
+    gathered, s_comm = None, None
+    if world > 1 and args.gather != 'none':
+        gathered = [torch.empty((world * c['rows'], pipe.out_dim),
+                                dtype=torch.float32, device='cuda')
+                    for c in chunks]
+        s_comm = torch.cuda.Stream()
+
+    ev_feat = []
+
+    def step(timed, seed):
+        cur = torch.cuda.current_stream()
+        for k, c in enumerate(chunks):
+            r0, r1 = c['row0'], c['row0'] + c['rows']
+            if timed:
+                pair = (torch.cuda.Event(enable_timing=True),
+                        torch.cuda.Event(enable_timing=True))
+                ev_feat.append(pair)
+                engine.feature_events = pair
+            pipe.run_device(
+                c['packed'], speakers=c['spk'] if pipe.cmvn == 'speaker'
+                else None, seed=seed, out=out[r0:r1], plans=plans,
+                base_buf=None if base is None else base[r0:r1],
+                batches=c['batches'])
+            engine.feature_events = None
+            if gathered is not None:
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(s_comm):
+                    s_comm.wait_event(done)
+                    dist.all_gather_into_tensor(gathered[k], out[r0:r1])
+        if gathered is not None:
+            cur.wait_stream(s_comm)      # the step ends with the collection
+
     for w in range(args.warmup):
-        step(seed=100 + w)
+        step(False, 100 + w)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -319,14 +535,15 @@ def main():
               torch.cuda.Event(enable_timing=True))
     e0.record()
     for i in range(args.steps):
-        step(i, seed=1000 + i)
+        step(True, 1000 + i)
     e1.record()
     barrier()
     t1 = time.time()
     launches = L.snb_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    ms_feat = float(np.mean([a.elapsed_time(b) for a, b in ev_feat]))
+    ms_feat = float(np.sum([a.elapsed_time(b) for a, b in ev_feat])
+                    / max(args.steps, 1))
     times = torch.tensor([ms_total, ms_feat], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -334,76 +551,48 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * total_frames / (ms_per_step * 1e-3)
 
-    # ---- end-to-end: pinned host PCM in, pinned host features out ----------
-    e2e = None
-    if not args.no_e2e:
-        host_pcm = torch.empty(pcm_dev.numel(), dtype=torch.int16,
-                               pin_memory=True)
-        host_pcm.copy_(pcm_dev)
-        out_host = torch.empty((total_frames, 39), dtype=torch.float32,
-                               pin_memory=True)
-        torch.cuda.synchronize()
-        # raw PCIe ceilings of this box (plain pinned copies, one direction)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        scratch = torch.empty_like(pcm_dev)
-        c0.record(); scratch.copy_(host_pcm, non_blocking=True); c1.record()
-        torch.cuda.synchronize()
-        h2d_gbs = host_pcm.numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        c0.record(); out_host.copy_(out, non_blocking=True); c1.record()
-        torch.cuda.synchronize()
-        d2h_gbs = out.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        del scratch
-        nrep = max(2, min(args.steps, 5))
-        for _ in range(2):                                           # warm-up
-            pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
-                          chunk_utts=args.chunk_utts)
-        barrier()
-        rep_ms = []
-        t_e0 = time.perf_counter()
-        for _ in range(nrep):
-            t_r = time.perf_counter()
-            pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
-                          chunk_utts=args.chunk_utts)
-            rep_ms.append((time.perf_counter() - t_r) * 1e3)
-        barrier()
-        dt = (time.perf_counter() - t_e0) / nrep
-        tt = torch.tensor([dt], device='cuda', dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt[0])
-        e2e = {'value': world * total_frames / dt, 'unit': 'frames/s',
-               'h2d_bytes_per_step': int(nutts * UTT_SAMPLES * 2),
-               'd2h_bytes_per_step': int(total_frames * 39 * 4),
-               'ms_per_step': dt * 1e3,
-               'ms_each_step': [round(t, 2) for t in rep_ms],
-               'api': 'FusedPipeline.run_host (chunked H2D/compute/D2H, '
-                      f'{args.chunk_utts} utterances per chunk)',
-               'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs}
-
-    # ---- collection (outside the step): NCCL all-gather of the feature blocks --
+    # ---- collection alone (N > 1): what the overlap hides --------------------
     gather = None
-    if world > 1:
-        from shennong_b200.distributed import gather_rows
-        full, _ = gather_rows(out)                                   # warm-up
-        del full
-        barrier()
+    if gathered is not None:
         g0, g1 = (torch.cuda.Event(enable_timing=True),
                   torch.cuda.Event(enable_timing=True))
+        barrier()
         g0.record()
         for _ in range(3):
-            full, _ = gather_rows(out)
-            del full
+            for k, c in enumerate(chunks):
+                dist.all_gather_into_tensor(
+                    gathered[k], out[c['row0']:c['row0'] + c['rows']])
         g1.record()
         barrier()
         gt = torch.tensor([g0.elapsed_time(g1) / 3], device='cuda',
                           dtype=torch.float64)
         dist.all_reduce(gt, op=dist.ReduceOp.MAX)
         nbytes = int(out.numel() * 4)
-        gather = {'ms': float(gt[0]), 'bytes_per_rank': nbytes,
-                  'recv_gbs_per_rank': (world - 1) * nbytes / (float(gt[0]) * 1e-3) / 1e9,
-                  'api': 'distributed.gather_rows (row counts + one NCCL '
-                         'all-gather of the [frames, 39] blocks; not part of '
-                         'the timed step)'}
+        gather = {'in_step': True, 'chunks': len(chunks),
+                  'alone_ms': float(gt[0]), 'bytes_per_rank': nbytes,
+                  'recv_gbs_per_rank':
+                  (world - 1) * nbytes / (float(gt[0]) * 1e-3) / 1e9,
+                  'api': 'all_gather_into_tensor of every chunk of the step '
+                         'on a second stream (NCCL over NVLink), chunk k '
+                         'travels while chunk k + 1 is computed; `alone_ms` '
+                         'is the same collection without compute'}
+
+    # ---- parity check on rows of every rank (dither 0, outside the clock) ---
+    check = parity_check(args, pipe, info, pcm_dev, host_head, rank, world,
+                         nutts, torch, dist, engine)
+
+    # ---- end-to-end: pinned host PCM in, pinned host features out ----------
+    e2e = None
+    if not args.no_e2e:
+        e2e = end_to_end(args, pipe, pcm_dev, out, starts, lengths, speakers,
+                         total_frames, world, barrier, torch, dist, stream)
+        if placement is not None:
+            e2e['host_placement'] = placement
+
+    # ---- the reference-facing API on WAV files -------------------------------
+    api = None
+    if not args.no_api:
+        api = api_leg(args, info, rank, world, barrier, torch, dist)
 
     if rank != 0:
         if world > 1:
@@ -411,44 +600,282 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    feat_gbs = total_frames * BYTES_PER_FRAME_KERNEL / (ms_feat * 1e-3) / 1e9
+    kernel_bpf = 320 + 4 * pipe.base_dim
+    feat_gbs = total_frames * kernel_bpf / (ms_feat * 1e-3) / 1e9
     roofline = {
         'bound': 'hbm', 'kernel': 'fused_features_512_kernel',
         'achieved': feat_gbs, 'peak': peak, 'unit': 'GB/s',
         'frac': feat_gbs / peak,
-        'traffic': int(total_frames * NCU_TRAFFIC_BYTES_PER_FRAME),
-        'traffic_source': TRAFFIC_SOURCE,
+        'traffic': (int(total_frames * NCU_TRAFFIC_BYTES_PER_FRAME)
+                    if args.config == 2 else None),
+        'traffic_source': TRAFFIC_SOURCE if args.config == 2 else None,
         'peak_source': peak_src,
-        'algorithmic_bytes_per_launch': int(total_frames * BYTES_PER_FRAME_KERNEL),
+        'algorithmic_bytes_per_launch': int(
+            total_frames * kernel_bpf / len(chunks)),
+        'launches_per_step': len(chunks),
         'kernel_ms': ms_feat,
+        'kernel_share_of_step': ms_feat / ms_per_step,
         'note': ('the chain is instruction-issue / shared-memory bound (~17 '
-                 'kflop/frame, AI ~45 flop/B), not HBM bound: see limits and '
-                 'fp32_tflops'),
-        'limits': NCU_LIMITS,
+                 'kflop/frame, AI ~45 flop/B), not HBM bound: see '
+                 'fp32_tflops and profiles/'),
         'fp32_tflops': total_frames * FLOPS_PER_FRAME / (ms_feat * 1e-3) / 1e12,
-        'pipeline_gbs': total_frames * BYTES_PER_FRAME_PIPELINE
+        'pipeline_gbs': total_frames * (320 + 4 * pipe.out_dim)
         / (ms_per_step * 1e-3) / 1e9,
     }
     cpu = None
     if not args.no_cpu:
-        sample_utts = min(nutts, 2048)
-        host_sample = pcm_dev[:sample_utts * UTT_SAMPLES].cpu().numpy()
-        cpu, _, _ = cpu_baseline(host_sample, sample_utts, args.dither)
+        cpu, _, _ = cpu_baseline(args.config, host_head, nhost, args.dither)
 
     result = {
-        'metric': 'MFCC frames/sec', 'value': value, 'unit': 'frames/s',
+        'metric': info['metric'], 'value': value, 'unit': 'frames/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config, 'clocks': clocks,
         'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
-        'cpu_baseline': cpu,
+        'cpu_baseline': cpu, 'check': check,
     }
+    if api is not None:
+        result['e2e_api'] = api
     if gather is not None:
         result['gather'] = gather
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config_info(args):
+    """description of the configuration without touching the GPU library"""
+    names = {1: ('filterbank-40 frames/sec', 1000,
+                 'BASELINE configs[1]: FilterbankProcessor 40-mel'),
+             2: ('MFCC frames/sec', 10000,
+                 'BASELINE configs[2]: MfccProcessor (13 ceps, 23 mel, '
+                 'reference defaults) + CMVN per utterance (norm_vars) + '
+                 'DeltaPostProcessor(order=2, window=2)'),
+             3: ('PLP + Kaldi pitch frames/sec', 6250,
+                 'BASELINE configs[3]: PlpProcessor + KaldiPitchProcessor '
+                 '(+ post-processing) pipeline, 50 000 utterances over 8 GPUs'),
+             4: ('full pipeline frames/sec', 4500,
+                 'BASELINE configs[4]: speech-features full pipeline '
+                 '(filterbank + Kaldi pitch + delta + CMVN by speaker with '
+                 'VAD), 100 h = 36 000 utterances over 8 GPUs')}
+    metric, utts, workload = names[args.config]
+    info = dict(metric=metric, utts=utts, workload=workload)
+    nutts = args.utts or utts
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    return None, dict(describe(args, info, nutts, world), metric=metric)
+
+
+def describe(args, info, nutts, world):
+    return {
+        'workload': info['workload'] + f' on {nutts} synthetic 16 kHz 10 s '
+        'utterances per GPU',
+        'baseline_config': args.config,
+        'utterances_per_gpu': nutts, 'frames_per_utterance': FRAMES_PER_UTT,
+        'dither': args.dither,
+        'sharding': f'utterances x{world}, no data-path collective; '
+        'collection (all-gather of the rows) inside the step for N > 1',
+        'l2': 'inputs (320 KB per utterance, GBs per GPU) larger than the '
+        '126 MB L2',
+    }
+
+
+def parity_check(args, pipe, info, pcm_dev, host_head, rank, world, nutts,
+                 torch, dist, engine):
+    """dither-0 rows of the first utterances of EVERY rank (gathered over
+    NCCL for N > 1) against the CPU oracle, on rank 0"""
+    import oracle
+    ncheck = min(8, nutts)
+    cpipe, _ = make_config(args.config, 0.0)
+    if cpipe.pitch is not None:
+        cpipe.pitch[1].delta_pitch_noise_stddev = 0
+    if cpipe.energy is not None:
+        cpipe.energy.dither = 0
+    packed = engine.PackedAudio.from_packed(
+        None, np.arange(ncheck, dtype=np.int64) * UTT_SAMPLES,
+        np.full(ncheck, UTT_SAMPLES, dtype=np.int64), dev=pcm_dev)
+    rows, _, _, _ = cpipe.run_device(
+        packed, speakers=['s'] * ncheck if cpipe.cmvn == 'speaker' else None)
+    if world > 1:
+        full = torch.empty((world * rows.shape[0], rows.shape[1]),
+                           dtype=torch.float32, device='cuda')
+        dist.all_gather_into_tensor(full, rows.contiguous())
+    else:
+        full = rows
+    if rank != 0:
+        return None
+    full = full.cpu().numpy().reshape(world, ncheck, FRAMES_PER_UTT, -1)
+    kind, kw = info['oracle']
+    worst, worst_pitch = 0.0, 0.0
+    for r in range(world):
+        head = host_head if r == 0 else synth_host(r * nutts, ncheck)
+        sigs = [head[u * UTT_SAMPLES:(u + 1) * UTT_SAMPLES]
+                for u in range(ncheck)]
+        feats = [oracle.features(kind, sig, dither=0, **kw) for sig in sigs]
+        # per-column bound: 1e-4 of the largest base coefficient; a CMVN with
+        # variance normalisation divides column d by its standard deviation
+        scale = max(float(np.abs(f).max()) for f in feats)
+        if args.config == 2:
+            want = [oracle.deltas(oracle.cmvn_apply(
+                f, oracle.cmvn_accumulate(f))) for f in feats]
+            bound = [np.tile(1e-4 * scale / f.std(axis=0), 3) for f in feats]
+        elif args.config == 4:
+            stats = 0
+            for sig, f in zip(sigs, feats):
+                e = oracle.features('energy', sig, dither=0)
+                w = oracle.vad(e.astype(np.float32).reshape(-1, 1))
+                stats = stats + oracle.cmvn_accumulate(
+                    f, w.reshape(-1).astype(np.float32))
+            want = [oracle.deltas(oracle.cmvn_apply(f, stats)) for f in feats]
+            std = np.concatenate(feats).std(axis=0)
+            bound = [np.tile(1e-4 * scale / std, 3)] * ncheck
+        else:
+            want = feats
+            bound = [np.full(f.shape[1], 1e-4 * scale) for f in feats]
+        for u in range(ncheck):
+            got = full[r, u]
+            d = want[u].shape[1]
+            ratio = (np.abs(got[:, :d] - want[u]) / bound[u][None, :]).max()
+            worst = max(worst, float(ratio))
+            if pipe.pitch is not None:
+                post = oracle.process_pitch(oracle.pitch(sigs[u]))
+                worst_pitch = max(worst_pitch, float(
+                    np.abs(got[:, d:] - post).max()))
+    return {'ranks': world, 'utterances_per_rank': ncheck,
+            'max_err_over_bound': worst,
+            'bound': '1e-4 * max|base coefficient| per column, divided by '
+            'the column\'s standard deviation after a variance-normalising '
+            'CMVN',
+            'max_abs_err_pitch_columns':
+            worst_pitch if pipe.pitch is not None else None,
+            'ok': bool(worst <= 1.0 and worst_pitch <= 1e-4),
+            'note': 'dither 0, oracle = CPU restatement (oracle/); pitch '
+            'columns come from the bit-exact state sequence'}
+
+
+def end_to_end(args, pipe, pcm_dev, out, starts, lengths, speakers,
+               total_frames, world, barrier, torch, dist, stream):
+    nutts = len(lengths)
+    host_pcm = torch.empty(pcm_dev.numel(), dtype=torch.int16, pin_memory=True)
+    host_pcm.copy_(pcm_dev)
+    out_host = torch.empty((total_frames, pipe.out_dim), dtype=torch.float32,
+                           pin_memory=True)
+    torch.cuda.synchronize()
+    # ceilings of this box: plain pinned copies, one direction each, then both
+    # directions at once -- every rank at the same time (what the host can
+    # deliver to N GPUs together)
+    c0, c1 = (torch.cuda.Event(enable_timing=True),
+              torch.cuda.Event(enable_timing=True))
+    scratch = torch.empty_like(pcm_dev)
+    barrier()
+    c0.record(); scratch.copy_(host_pcm, non_blocking=True); c1.record()
+    barrier()
+    h2d_gbs = host_pcm.numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    c0.record(); out_host.copy_(out, non_blocking=True); c1.record()
+    barrier()
+    d2h_gbs = out.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    s2 = torch.cuda.Stream()
+    barrier()
+    t_b = time.perf_counter()
+    scratch.copy_(host_pcm, non_blocking=True)
+    with torch.cuda.stream(s2):
+        out_host.copy_(out, non_blocking=True)
+    barrier()
+    both_s = time.perf_counter() - t_b
+    tb = torch.tensor([both_s], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    both_s = float(tb[0])
+    del scratch
+    spk = speakers if pipe.cmvn == 'speaker' else None
+    nrep = max(2, min(args.steps, 5))
+    for _ in range(2):                                           # warm-up
+        pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
+                      chunk_utts=args.chunk_utts, speakers=spk)
+    barrier()
+    rep_ms = []
+    t_e0 = time.perf_counter()
+    for _ in range(nrep):
+        t_r = time.perf_counter()
+        pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
+                      chunk_utts=args.chunk_utts, speakers=spk)
+        rep_ms.append((time.perf_counter() - t_r) * 1e3)
+    barrier()
+    dt = (time.perf_counter() - t_e0) / nrep
+    tt = torch.tensor([dt], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    return {'value': world * total_frames / dt, 'unit': 'frames/s',
+            'h2d_bytes_per_step': int(nutts * UTT_SAMPLES * 2),
+            'd2h_bytes_per_step': int(total_frames * pipe.out_dim * 4),
+            'ms_per_step': dt * 1e3,
+            'ms_each_step': [round(t, 2) for t in rep_ms],
+            'api': 'FusedPipeline.run_host (stream.StreamRunner: chunked '
+                   f'H2D / compute / D2H, {args.chunk_utts} utterances per '
+                   'chunk; every rank returns the rows of its shard)',
+            'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs,
+            'host_ceiling_ms': both_s * 1e3,
+            'fraction_of_host_ceiling': both_s / dt,
+            'ceiling': 'the same H2D + D2H bytes as plain concurrent pinned '
+                       'copies, all ranks at once, no compute'}
+
+
+def api_leg(args, info, rank, world, barrier, torch, dist):
+    """The calls a user of the reference makes, on WAV files: process_all of
+    the main features processor and pipeline.extract_features of the
+    configuration (sharded over the ranks; every rank gets every row)"""
+    import scipy.io.wavfile
+    from shennong_b200 import Utterances, pipeline
+    from shennong_b200.processor import MfccProcessor
+    n = args.api_utts
+    root = os.path.join(tempfile.gettempdir(), 'snb_bench_wavs_%d' % n)
+    if rank == 0:
+        os.makedirs(root, exist_ok=True)
+        pcm = synth_host(0, n)
+        for u in range(n):
+            path = os.path.join(root, 'u%05d.wav' % u)
+            if not os.path.exists(path):
+                scipy.io.wavfile.write(
+                    path, SAMPLE_RATE,
+                    pcm[u * UTT_SAMPLES:(u + 1) * UTT_SAMPLES])
+    barrier()
+    utts = Utterances([('u%05d' % u, os.path.join(root, 'u%05d.wav' % u),
+                        'spk%03d' % (u // UTTS_PER_SPEAKER))
+                       for u in range(n)])
+    cores = len(os.sched_getaffinity(0))
+    results = {}
+    proc = MfccProcessor(dither=args.dither)
+    config = pipeline.get_default_config(
+        'mfcc', with_cmvn=True, with_delta=True)
+    config['mfcc']['dither'] = args.dither
+
+    def timed(name, call, dim):
+        call()                                                  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        feats = call()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        frames = sum(f.nframes for f in feats.values())
+        results[name] = {'value': frames / float(tt[0]), 'unit': 'frames/s',
+                         'ms': float(tt[0]) * 1e3, 'utterances': len(feats),
+                         'frames': frames, 'dim': dim, 'njobs': cores}
+    timed('MfccProcessor.process_all',
+          lambda: proc.process_all(utts, njobs=cores), 13)
+    timed('pipeline.extract_features (mfcc + cmvn by speaker with vad + delta)',
+          lambda: pipeline.extract_features(config, utts, njobs=cores), 39)
+    results['note'] = (
+        f'{n} WAV files of 10 s read from {tempfile.gettempdir()} inside the '
+        'timed call (mono 16-bit PCM payloads go straight into pinned '
+        'staging), rows of all ranks gathered to every rank, one Features '
+        'per utterance')
+    if rank == 0 and os.environ.get('SNB_BENCH_KEEP_WAVS') is None:
+        shutil.rmtree(root, ignore_errors=True)
+    return results
 
 
 if __name__ == '__main__':

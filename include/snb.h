@@ -319,6 +319,28 @@ int snb_process_pitch(const snb_pitch_post_opts *o, const float *d_raw,
                       int64_t max_frames_per_utt, uint64_t seed, float *d_out,
                       int64_t ld_out, void *stream);
 
+/* ---- collection: all-gather of the finished rows over NVLink ----
+ * The reference collects the per-utterance results of its joblib workers in
+ * the parent process (pipeline.py:541-567, processor/base.py:97-107).  One
+ * process per GPU here: every rank owns a result buffer, its peers map it
+ * through CUDA IPC, and a rank PUSHES its finished row blocks into the buffers
+ * of all ranks with one kernel of plain stores over NVLink / NVSwitch. */
+typedef struct snb_peer_handle { unsigned char bytes[64]; } snb_peer_handle;
+/* device buffer of `bytes` + the handle other processes of the node open it with */
+int snb_peer_buffer_create(int64_t bytes, void **d_ptr, snb_peer_handle *handle);
+/* maps a peer's buffer in this process (enables peer access); close before exit */
+int snb_peer_buffer_open(const snb_peer_handle *handle, void **d_ptr);
+int snb_peer_buffer_close(void *d_ptr);
+int snb_peer_buffer_destroy(void *d_ptr);
+/* copies nfloats (multiple of 4) contiguous floats at d_src to
+ * dst[p] + dst_offset_floats for p < ndst (HOST array of DEVICE pointers, own
+ * buffer and mapped peer buffers alike; ndst <= 16), by `ctas` CTAs (<= 0: 32)
+ * on `stream`.  The rows are visible to a peer once this launch has completed
+ * and the ranks have synchronised. */
+int snb_gather_rows(const float *d_src, int64_t nfloats, float *const *dst,
+                    int32_t ndst, int64_t dst_offset_floats, int32_t ctas,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

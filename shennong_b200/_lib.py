@@ -141,6 +141,11 @@ SIGNATURES = {
     'snb_process_pitch_dim': (i32, [vp]),
     'snb_process_pitch': (ctypes.c_int, [vp, vp, i64, vp, vp, i64, i64, i64,
                                          u64, vp, i64, vp]),
+    'snb_peer_buffer_create': (ctypes.c_int, [i64, vp, vp]),
+    'snb_peer_buffer_open': (ctypes.c_int, [vp, vp]),
+    'snb_peer_buffer_close': (ctypes.c_int, [vp]),
+    'snb_peer_buffer_destroy': (ctypes.c_int, [vp]),
+    'snb_gather_rows': (ctypes.c_int, [vp, i64, vp, i32, i64, i32, vp]),
 }
 
 _lib = None

@@ -81,7 +81,7 @@ class Audio:
 
     # -- files ---------------------------------------------------------------
     @classmethod
-    @functools.lru_cache()
+    @functools.lru_cache(maxsize=None)
     def scan(cls, filename):
         """Metadata (nchannels, sample_rate, nsamples, duration) of a WAV file
 
@@ -103,6 +103,44 @@ class Audio:
                 nchannels, int(rate), data.shape[0], data.shape[0] / rate)
         except Exception:
             raise ValueError(f'cannot scan audio file {filename}') from None
+
+    @classmethod
+    @functools.lru_cache(maxsize=None)
+    def wav_layout(cls, filename):
+        """(data offset in bytes, nsamples, sample rate) of a mono 16-bit PCM
+        WAV file, None for anything else (compressed, float, multi-channel, malformed):
+        the batch entry points read such payloads straight into the pinned
+        staging buffer the GPU copies from (shennong_b200.stream.AudioSource)
+        instead of going through ``load`` (reference: audio.py:243-286)"""
+        try:
+            with open(str(filename), 'rb') as fh:
+                head = fh.read(12)
+                if head[:4] != b'RIFF' or head[8:12] != b'WAVE':
+                    return None
+                fmt = None
+                while True:
+                    chunk = fh.read(8)
+                    if len(chunk) < 8:
+                        return None
+                    size = int.from_bytes(chunk[4:8], 'little')
+                    if chunk[:4] == b'fmt ':
+                        fmt = fh.read(size + (size & 1))[:16]
+                    elif chunk[:4] == b'data':
+                        if fmt is None or len(fmt) < 16:
+                            return None
+                        tag = int.from_bytes(fmt[0:2], 'little')
+                        nchannels = int.from_bytes(fmt[2:4], 'little')
+                        rate = int.from_bytes(fmt[4:8], 'little')
+                        bits = int.from_bytes(fmt[14:16], 'little')
+                        if tag != 1 or nchannels != 1 or bits != 16:
+                            return None
+                        offset = fh.tell()
+                        left = os.path.getsize(str(filename)) - offset
+                        return offset, min(size, left) // 2, rate
+                    else:
+                        fh.seek(size + (size & 1), 1)
+        except OSError:
+            return None
 
     @classmethod
     @functools.lru_cache(maxsize=2)

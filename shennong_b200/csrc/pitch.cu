@@ -41,8 +41,9 @@ struct PitchTables {
   std::vector<float> lags, pen;                 // [nstates]
   std::vector<int32_t> up_first, up_nw;         // [nstates]
   std::vector<float> up_w;                      // [nstates, up_nw_max]
-  int32_t ns4, ns_pad;                          // nstates rounded up to 4 (cost rows) / 2 (tap rows)
-  std::vector<double> up_w_t;                   // [up_nw_max, ns_pad] same taps, state-contiguous doubles
+  int32_t ns4, nwp;                             // nstates rounded up to 4 (cost rows); up_nw_max | 1
+  std::vector<double> up_w_t;                   // [nstates, nwp] same taps as doubles (odd row stride:
+                                                // conflict-free 64-bit loads by consecutive states)
   // device copies (one allocation)
   void *d_blob = nullptr;
   const int32_t *d_down_first, *d_down_nw, *d_up_first, *d_up_nw;
@@ -188,11 +189,11 @@ int pitch_plan_init(snb_plan *plan) {
   for (int32_t i = 0; i < t->nstates; ++i)
     std::copy(uw[i].begin(), uw[i].end(), t->up_w.begin() + static_cast<size_t>(i) * t->up_nw_max);
   t->ns4 = (t->nstates + 3) & ~3;
-  t->ns_pad = (t->nstates + 1) & ~1;
-  t->up_w_t.assign(static_cast<size_t>(t->up_nw_max) * t->ns_pad, 0.0);
+  t->nwp = t->up_nw_max | 1;
+  t->up_w_t.assign(static_cast<size_t>(t->nstates) * t->nwp, 0.0);
   for (int32_t i = 0; i < t->nstates; ++i)
     for (int32_t j = 0; j < t->up_nw[i]; ++j)
-      t->up_w_t[static_cast<size_t>(j) * t->ns_pad + i] = static_cast<double>(uw[i][j]);
+      t->up_w_t[static_cast<size_t>(i) * t->nwp + j] = static_cast<double>(uw[i][j]);
   // --- Viterbi transition penalties: (i-j)^2 * inter_frame_factor ---
   const float delta_pitch_sq = static_cast<float>(std::pow(std::log(1.0 + static_cast<double>(o.delta_pitch)), 2.0));
   const float factor = delta_pitch_sq * o.penalty_factor;
@@ -407,11 +408,11 @@ struct NccfArgs {
   const int64_t *gfo;           // [nutts+1] cumulated frames in that order
   const float *ballast;         // [nutts,2]
   int64_t k0, k1, q0, q1;       // group: sorted utterances [k0,k1), frames [q0,q1)
-  int32_t first_lag, nmeas, nstates, ns4, shift, basic_len, full_len, nw, ns_pad;
+  int32_t first_lag, nmeas, nstates, ns4, shift, basic_len, full_len, nw, nwp;
   int32_t snip_edges, table_in_smem;
   float preemph, soft_min_f0;
   const float *lags;
-  const double *up_w_t;         // [nw, ns_pad] taps, state-contiguous
+  const double *up_w_t;         // [ns, nwp] taps
   const int32_t *up_first;
   float *cost, *pov;
 };
@@ -428,31 +429,36 @@ __host__ __device__ inline NccfSmem nccf_smem_layout(int full_len, int nm, int n
   s.total = off;
   return s;
 }
-__host__ __device__ inline int nccf_shared_words(int ns, int ns_pad, int nw, bool table) {
-  return (table ? 2 * nw * ns_pad : 0) + 2 * ((ns + 1) & ~1);   // taps (doubles), up_first, soft_min_f0*lag
+__host__ __device__ inline int nccf_shared_words(int ns, int nwp, bool table) {
+  return (table ? 2 * (((ns * nwp) + 1) & ~1) : 0) + 2 * ((ns + 1) & ~1);   // taps (doubles), up_first, soft_min_f0*lag
 }
 
+// NWC > 0: number of upsampling taps known at compile time (10 for Kaldi's
+// defaults) and the tap table in shared memory; 0: any tap count, table in
+// shared memory when it fits, else read through L1
+template <int NWC>
 __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarp_cta = blockDim.x >> 5;
-  const int ns = a.nstates, nm = a.nmeas, bl = a.basic_len, fl = a.full_len, nw = a.nw;
+  const int ns = a.nstates, nm = a.nmeas, bl = a.basic_len, fl = a.full_len;
+  const int nw = NWC > 0 ? NWC : a.nw, nwp = nw | 1;
+  const bool table = NWC > 0 || a.table_in_smem;
   // ---- CTA-shared tables ----
   double *s_upw = reinterpret_cast<double *>(smem_raw);
-  const int tab_words = a.table_in_smem ? 2 * nw * a.ns_pad : 0;
+  const int tab_words = table ? 2 * (((ns * nwp) + 1) & ~1) : 0;
   int32_t *s_upfirst = reinterpret_cast<int32_t *>(smem_raw) + tab_words;
   float *s_lagc = reinterpret_cast<float *>(s_upfirst + ((ns + 1) & ~1));
-  if (a.table_in_smem)
-    for (int i = tid; i < nw * a.ns_pad; i += blockDim.x) s_upw[i] = a.up_w_t[i];
+  if (table)
+    for (int i = tid; i < ns * nwp; i += blockDim.x) s_upw[i] = a.up_w_t[i];
   for (int i = tid; i < ns; i += blockDim.x) {
     s_upfirst[i] = min(max(a.up_first[i], 0), nm - 1);       // (a state without taps has zero weights)
     s_lagc[i] = __fmul_rn(a.soft_min_f0, a.lags[i]);
   }
   __syncthreads();
-  const double *upw = a.table_in_smem ? s_upw : a.up_w_t;
   // ---- warp-private buffers ----
   const NccfSmem L = nccf_smem_layout(fl, nm, nw);
-  double *wbase = reinterpret_cast<double *>(smem_raw + 4 * static_cast<size_t>(nccf_shared_words(ns, a.ns_pad, nw, a.table_in_smem))) +
+  double *wbase = reinterpret_cast<double *>(smem_raw + 4 * static_cast<size_t>(nccf_shared_words(ns, nwp, table))) +
                   static_cast<size_t>(warp) * L.total;
   double *w_z = wbase + L.z, *w_pre = wbase + L.pre, *w_np = wbase + L.np;
   for (int i = fl + lane; i < fl + 6; i += 32) w_z[i] = 0.0;
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
         double in0 = 0.0, in1 = 0.0, in2 = 0.0;
         double r0 = zq[0], r1 = zq[1];
         int i = 0;
-#pragma unroll 1
+#pragma unroll 5
         for (; i + 3 < bl; i += 4) {
           const double2 wa = *reinterpret_cast<const double2 *>(w_z + i);
           const double2 wb = *reinterpret_cast<const double2 *>(w_z + i + 2);
@@ -597,18 +603,29 @@ __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
       }
       __syncwarp();
       // ---- upsample to the log-spaced lags (taps padded with zero weights to nw); local cost ----
-      float *crow = a.cost + qrel * a.ns4;
-      for (int i = lane; i < ns; i += 32) {
+      float *crow = a.cost + qrel * a.ns4 + lane;
+#pragma unroll 2
+      for (int i = lane; i < ns; i += 32, crow += 32) {
         const double *src = w_np + s_upfirst[i];
-        const double *w = upw + i;
         double acc = 0.0;
-#pragma unroll 5
-        for (int j = 0; j < nw; ++j) acc = fma(w[static_cast<size_t>(j) * a.ns_pad], src[j], acc);
+        if (NWC > 0) {
+          const double *w = s_upw + i * nwp;
+#pragma unroll
+          for (int j = 0; j < NWC; ++j) acc = fma(w[j], src[j], acc);
+        } else if (table) {
+          const double *w = s_upw + i * nwp;
+#pragma unroll 2
+          for (int j = 0; j < nw; ++j) acc = fma(w[j], src[j], acc);
+        } else {
+          const double *w = a.up_w_t + static_cast<int64_t>(i) * nwp;
+#pragma unroll 2
+          for (int j = 0; j < nw; ++j) acc = fma(__ldg(w + j), src[j], acc);
+        }
         const float nccf = static_cast<float>(acc);
         // local_cost = 1 - nccf; local_cost += soft_min_f0 * lag * nccf
         float c = __fadd_rn(1.0f, -nccf);
         c = __fadd_rn(__fmul_rn(s_lagc[i], nccf), c);
-        crow[i] = c;
+        *crow = c;
       }
     }
   }
@@ -649,7 +666,7 @@ struct TrackArgs {
   const float *cost, *pov;
   const int64_t *order, *gfo, *frame_offsets;
   int64_t k0, k1, q0;
-  int32_t nstates, ns4, nmeas, nw, ns_pad;
+  int32_t nstates, ns4, nmeas, nw, nwp;
   const float *lags, *pen;
   const double *up_w_t;
   const int32_t *up_first;
@@ -849,13 +866,12 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_viterbi_kernel(c
       for (int64_t f = lane; f < F; f += 32) {
         const int sidx = states[f];
         const int first = min(max(a.up_first[sidx], 0), nm - 1);
-        const double *w = a.up_w_t + sidx;
+        const double *w = a.up_w_t + static_cast<int64_t>(sidx) * a.nwp;
         const float *pv = prow + f * nm + first;
         const int n = min(nw, nm - first);                     // taps beyond are zero weights
         double acc = 0.0;
 #pragma unroll 1
-        for (int j = 0; j < n; ++j)
-          acc = fma(w[static_cast<size_t>(j) * a.ns_pad], static_cast<double>(pv[j]), acc);
+        for (int j = 0; j < n; ++j) acc = fma(w[j], static_cast<double>(pv[j]), acc);
         float *o = a.out + (row0 + f) * a.ld_out;
         o[0] = static_cast<float>(acc);
         o[1] = __fdiv_rn(1.0f, a.lags[sidx]);
@@ -1030,10 +1046,10 @@ struct NccfShape { int warps; bool table; size_t smem; };
 static NccfShape nccf_shape(const PitchTables *t) {
   NccfShape s;
   const NccfSmem L = nccf_smem_layout(t->full_len, t->nmeas, t->up_nw_max);
-  s.table = static_cast<size_t>(2 * t->up_nw_max) * t->ns_pad * 4 <= 96 * 1024;
+  s.table = t->up_nw_max == 10 || static_cast<size_t>(t->nstates) * t->nwp * 8 <= 96 * 1024;
   s.warps = 16;
   for (;;) {
-    s.smem = static_cast<size_t>(nccf_shared_words(t->nstates, t->ns_pad, t->up_nw_max, s.table)) * 4 +
+    s.smem = static_cast<size_t>(nccf_shared_words(t->nstates, t->nwp, s.table)) * 4 +
              static_cast<size_t>(s.warps) * L.total * 8 + 16;
     if (s.smem <= 110 * 1024 || s.warps == 1) break;        // two CTAs per SM when possible
     s.warps >>= 1;
@@ -1191,8 +1207,10 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   SNB_LAUNCH_CHECK();
 
   const NccfShape nshape = nccf_shape(t);
-  static std::atomic<size_t> nccf_cur{48 * 1024}, track_cur{48 * 1024};
-  int rc = raise_smem(pitch_nccf_kernel, nccf_cur, nshape.smem);
+  static std::atomic<size_t> nccf_cur{48 * 1024}, nccf_cur0{48 * 1024}, track_cur{48 * 1024};
+  const bool nw10 = t->up_nw_max == 10 && nshape.table;     // Kaldi's default resampling options
+  int rc = nw10 ? raise_smem(pitch_nccf_kernel<10>, nccf_cur, nshape.smem)
+                : raise_smem(pitch_nccf_kernel<0>, nccf_cur0, nshape.smem);
   if (rc != SNB_OK) return rc;
   const size_t tsmem = track_smem(t, warps);
   rc = raise_smem(pitch_viterbi_kernel, track_cur, tsmem);
@@ -1208,7 +1226,7 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
       n.k0 = k0; n.k1 = k1; n.q0 = q0; n.q1 = q1;
       n.first_lag = t->first_lag; n.nmeas = t->nmeas; n.nstates = t->nstates; n.ns4 = t->ns4;
       n.shift = t->shift; n.basic_len = t->basic_len; n.full_len = t->full_len;
-      n.nw = t->up_nw_max; n.ns_pad = t->ns_pad;
+      n.nw = t->up_nw_max; n.nwp = t->nwp;
       n.snip_edges = plan->po.snip_edges; n.table_in_smem = nshape.table ? 1 : 0;
       n.preemph = plan->po.preemph_coeff; n.soft_min_f0 = plan->po.soft_min_f0;
       n.lags = t->d_lags; n.up_w_t = t->d_up_w_t; n.up_first = t->d_up_first;
@@ -1216,14 +1234,15 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
       const int64_t ntasks = (q1 - q0 + kNccfTask - 1) / kNccfTask;
       const int64_t want = (ntasks + nshape.warps - 1) / nshape.warps;
       const unsigned ngrid = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * 2));
-      pitch_nccf_kernel<<<ngrid, nshape.warps * 32, nshape.smem, stream>>>(n);
+      if (nw10) pitch_nccf_kernel<10><<<ngrid, nshape.warps * 32, nshape.smem, stream>>>(n);
+      else pitch_nccf_kernel<0><<<ngrid, nshape.warps * 32, nshape.smem, stream>>>(n);
       SNB_LAUNCH_CHECK();
 
       TrackArgs a;
       a.cost = cost; a.pov = pov;
       a.order = d_order; a.gfo = d_gfo; a.frame_offsets = batch->d_frame_offsets;
       a.k0 = k0; a.k1 = k1; a.q0 = q0;
-      a.nstates = t->nstates; a.ns4 = t->ns4; a.nmeas = t->nmeas; a.nw = t->up_nw_max; a.ns_pad = t->ns_pad;
+      a.nstates = t->nstates; a.ns4 = t->ns4; a.nmeas = t->nmeas; a.nw = t->up_nw_max; a.nwp = t->nwp;
       a.lags = t->d_lags; a.pen = t->d_pen; a.up_w_t = t->d_up_w_t; a.up_first = t->d_up_first;
       a.bp = bp; a.states = states; a.max_frames = mf;
       a.out = d_out; a.ld_out = ld_out;

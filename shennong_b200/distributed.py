@@ -123,6 +123,18 @@ def gather_rows(local, group=None):
     return torch.cat(blocks, dim=0), counts_host
 
 
+def all_gather_objects(obj, group=None):
+    """[obj of rank 0, ..., obj of rank n-1] on every rank (small host
+    objects: CMVN statistics, speaker indices)"""
+    dist = _dist()
+    size = world()[1]
+    if size == 1:
+        return [obj]
+    out = [None] * size
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
 def allreduce_stats(stats, group=None):
     """Sums float64 CMVN statistics [G, 2, d+1] over the ranks (only needed
     when a speaker is split across GPUs)"""

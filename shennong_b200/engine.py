@@ -202,9 +202,23 @@ class Batch:
 # --------------------------------------------------------------------------
 # kernel launches (all asynchronous on torch's current stream)
 # --------------------------------------------------------------------------
+# optional (start, end) CUDA events recorded around the NEXT feature launch
+# on torch's current stream (bench.py times the dominant kernel live, inside
+# the timed step, with them)
+feature_events = None
+
+
 def compute_features(plan, batch, seed=0, out=None, float64=False):
     """[total_frames, dim] features of the batch (device tensor)"""
+    global feature_events
     torch = require_cuda()
+    events, feature_events = feature_events, None
+    if events is not None:
+        events[0].record()
+        try:
+            return compute_features(plan, batch, seed, out, float64)
+        finally:
+            events[1].record()
     dtype = torch.float64 if float64 else torch.float32
     if out is None:
         out = torch.empty((batch.total_frames, plan.dim), dtype=dtype,
@@ -274,12 +288,17 @@ def deltas(x, layout, order, window, norm=None, utt_group=None, out=None):
     return out
 
 
-def cmvn_accumulate(x, layout, weights=None):
+def cmvn_accumulate(x, layout, weights=None, out=None):
     """Per-utterance CMVN statistics, float64 [nutts, 2, dim+1]"""
     torch = require_cuda()
     dim = x.shape[1]
-    stats = torch.empty((layout.nutts, 2, dim + 1), dtype=torch.float64,
-                        device='cuda')
+    stats = out
+    if stats is None:
+        stats = torch.empty((layout.nutts, 2, dim + 1), dtype=torch.float64,
+                            device='cuda')
+    elif (tuple(stats.shape) != (layout.nutts, 2, dim + 1)
+          or not stats.is_contiguous()):
+        raise ValueError('bad statistics buffer')
     _lib.check(_lib.lib().snb_cmvn_accumulate(
         _ptr(x), x.stride(0), dim, layout.ptr, layout.nutts, _ptr(weights),
         _ptr(stats), _stream_ptr()))
@@ -401,6 +420,17 @@ def num_frames_array(frame_opts, lengths):
         return np.where(lengths < size, 0, 1 + (lengths - size) // shift)
     return (lengths + shift // 2) // shift
 
+
+
+def pitch_num_frames_array(pitch_opts, lengths):
+    """snb_pitch_num_frames (frames compute_kaldi_pitch returns,
+    pitch_kaldi.py:298) for an int64 array of utterance lengths"""
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    out = np.empty(len(lengths), dtype=np.int64)
+    _lib.lib().snb_pitch_num_frames_array(
+        _lib.np_ptr(lengths), len(lengths), _lib.ref(pitch_opts),
+        _lib.np_ptr(out))
+    return out
 
 
 _seed_lock = threading.Lock()

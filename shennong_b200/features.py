@@ -23,10 +23,30 @@ class Features:
         if validate is True:
             self.validate()
 
+    @classmethod
+    def _deferred(cls, data, times, properties):
+        """Features whose `times` and `properties` are zero-argument
+        callables evaluated at first access: the batch entry points wrap the
+        rows of tens of thousands of utterances without building their
+        timestamps and property dicts up front"""
+        return cls(data, times, properties, validate=False)
+
     data = property(lambda self: self._data, doc='the features matrix')
-    times = property(lambda self: self._times, doc='frames timestamps')
-    properties = property(
-        lambda self: self._properties, doc='metadata of the features')
+
+    @property
+    def times(self):
+        """frames timestamps"""
+        if callable(self._times):
+            self._times = self._times()
+        return self._times
+
+    @property
+    def properties(self):
+        """metadata of the features"""
+        if callable(self._properties):
+            self._properties = self._properties()
+        return self._properties
+
     dtype = property(lambda self: self.data.dtype)
     shape = property(lambda self: self.data.shape)
     ndims = property(lambda self: self.shape[1])

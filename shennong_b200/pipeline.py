@@ -24,7 +24,7 @@ import textwrap
 import numpy as np
 import yaml
 
-from shennong_b200 import engine
+from shennong_b200 import engine, stream
 from shennong_b200.features import Features
 from shennong_b200.features_collection import FeaturesCollection
 from shennong_b200.fused import FusedPipeline
@@ -230,7 +230,7 @@ class _Carrier:
 
 
 def extract_features(configuration, utterances, warps=None, njobs=1,
-                     log=get_logger('pipeline', 'warning')):
+                     log=get_logger('pipeline', 'warning'), gather=True):
     """Extracts the features of all the `utterances`
 
     Parameters
@@ -243,8 +243,19 @@ def extract_features(configuration, utterances, warps=None, njobs=1,
     warps : dict, optional
         Known VTLN warps indexed by utterance name or by speaker
     njobs : int, optional
-        Host threads used to load the audio files (the extraction itself is
-        batched on the GPU)
+        Host threads that read the audio into the pinned staging buffers
+        (the extraction itself is batched on the GPU)
+    gather : bool, optional
+        Only under ``torch.distributed`` (one process per GPU): every rank
+        extracts its own shard of the utterances (whole speakers when CMVN
+        is by speaker); with `gather` the rows of all ranks are all-gathered
+        over NCCL while the extraction proceeds and every rank returns the
+        complete collection, else each rank returns its shard.
+
+    The corpus is streamed: utterances are read, uploaded, processed and
+    downloaded in chunks, so that neither device memory nor pinned host
+    staging grow with the corpus (the reference streams utterance by
+    utterance, pipeline.py:541-567); only the result lives in host memory.
 
     Returns
     -------
@@ -266,33 +277,149 @@ def extract_features(configuration, utterances, warps=None, njobs=1,
         manager.warps = warps
 
     utts = list(utterances)
-    if njobs > 1 and len(utts) > 1:
-        with concurrent.futures.ThreadPoolExecutor(njobs) as pool:
-            audios = list(pool.map(manager.get_audio, utts))
-    else:
-        audios = [manager.get_audio(u) for u in utts]
-
-    # one fused batch per sample rate (plans depend on it)
-    out = {}
-    rates = sorted(set(a.sample_rate for a in audios))
-    groups = []
-    for rate in rates:
-        idx = [i for i, a in enumerate(audios) if a.sample_rate == rate]
-        groups.append(([utts[i] for i in idx], [audios[i] for i in idx]))
+    rate_of = {f: m.sample_rate for f, m in manager.audio_metadata.items()}
+    rates = sorted(set(rate_of[u.audio_file] for u in utts))
+    groups = [[u for u in utts if rate_of[u.audio_file] == rate]
+              for rate in rates]
     by_speaker = 'cmvn' in config and config['cmvn']['by_speaker']
     spans = len(groups) > 1 and by_speaker and any(
-        len({g for g, (gu, _) in enumerate(groups)
+        len({g for g, gu in enumerate(groups)
              if any(u.speaker == spk for u in gu)}) > 1
         for spk in {u.speaker for u in utts})
+    out = {}
     if spans:
         # a speaker has utterances at several sample rates: its CMVN statistics
         # are pooled over all of them (pipeline.py:541-557 accumulates per
         # speaker whatever the rate; test/test_pipeline.py:347-420)
-        out = _extract_groups_pooled_speakers(manager, groups, log)
+        loaded = [(gu, _load_audios(manager, gu, njobs)) for gu in groups]
+        out = _extract_groups_pooled_speakers(manager, loaded, log)
     else:
-        for gutts, gaudios in groups:
-            out.update(_extract_group(manager, gutts, gaudios, log))
-    return FeaturesCollection((u.name, out[u.name]) for u in utts)
+        for gutts in groups:
+            out.update(_extract_group_streamed(
+                manager, gutts, log, njobs, gather))
+    return FeaturesCollection(
+        (u.name, out[u.name]) for u in utts if u.name in out)
+
+
+def _load_audios(manager, utts, njobs):
+    if njobs > 1 and len(utts) > 1:
+        with concurrent.futures.ThreadPoolExecutor(njobs) as pool:
+            return list(pool.map(manager.get_audio, utts))
+    return [manager.get_audio(u) for u in utts]
+
+
+def _extract_group_streamed(manager, utts, log, njobs, gather=True):
+    """Features of utterances that share a sample rate, streamed through the
+    fused pipeline in bounded memory (sharded over the ranks of
+    torch.distributed when initialised)"""
+    config = manager.config
+    proc = manager.get_features_processor(utts[0])
+    delta = manager.get_delta_processor() if 'delta' in config else None
+    cmvn_mode, vad, energy = None, None, None
+    if 'cmvn' in config:
+        cmvn_mode = 'speaker' if config['cmvn']['by_speaker'] else 'utterance'
+        if config['cmvn']['with_vad']:
+            vad = manager.get_vad_processor()
+            energy = manager.get_energy_processor(utts[0])
+    pitch = None
+    if 'pitch' in config:
+        pitch = (manager.get_pitch_processor(utts[0]),
+                 manager.get_pitch_post_processor())
+        pitch[1]._validate(2)
+    by_speaker = cmvn_mode == 'speaker'
+    if by_speaker:    # whole speakers are contiguous (blocks, shards)
+        order = np.argsort(np.asarray([u.speaker for u in utts]),
+                           kind='stable')
+        utts = [utts[i] for i in order]
+    items, lengths, int16 = stream.audio_items(utts)
+    if vad is not None and not int16:
+        # energy keeps the raw scale of float audio (energy.py:158): VAD on
+        # non-int16 audio goes through the per-utterance API
+        return _extract_group(manager, utts, _load_audios(
+            manager, utts, njobs), log)
+    has_warp = bool(manager.warps) and proc.name != 'spectrogram'
+    warp_of = [manager.get_warp(u) for u in utts] if has_warp else None
+    warps = np.asarray(warp_of, np.float32) if has_warp else None
+    speakers = [u.speaker for u in utts] if by_speaker else None
+    pipe = FusedPipeline(proc, delta=delta, cmvn=cmvn_mode, norm_vars=True,
+                         vad=vad, energy=energy, pitch=pitch)
+    data, parts = stream.extract_corpus(
+        pipe, items, lengths, speakers=speakers, warps=warps, njobs=njobs,
+        gather=gather)
+    result = {}
+    for index, plan, row0, stats, group in parts:
+        if stats is not None:
+            counts = stats[:, 0, -1]
+            if len(counts) and counts.min() < 1.0:
+                raise ValueError(
+                    'insufficient accumulation of stats for CMVN, '
+                    'must be >= 1.0 but is {}'.format(counts.min()))
+        for j, i in enumerate(index):
+            utt = utts[i]
+            a = row0 + int(plan.foffs[j])
+            block = data[a:a + int(plan.valid[j])]
+            st = None
+            if stats is not None:
+                st = stats[group[j] if group is not None else j]
+            warp = warp_of[i] if warp_of is not None else 1.0
+            result[utt.name] = Features._deferred(
+                block, _Times(proc, block.shape[0]),
+                _Properties(manager, proc, delta, pitch, cmvn_mode, utt,
+                            warp, st))
+    return result
+
+
+class _Times:
+    """frame timestamps of an utterance, built at first access"""
+    __slots__ = ('proc', 'nframes')
+
+    def __init__(self, proc, nframes):
+        self.proc, self.nframes = proc, nframes
+
+    def __call__(self):
+        return self.proc.times(self.nframes)
+
+
+class _Properties:
+    """properties of an utterance's features with the reference's layout
+    (pipeline.py:570-648), built at first access"""
+    __slots__ = ('args',)
+
+    def __init__(self, *args):
+        self.args = args
+
+    def __call__(self):
+        manager, proc, delta, pitch, cmvn_mode, utt, warp, stats = self.args
+        props = (proc.get_properties() if proc.name == 'spectrogram'
+                 else proc.get_properties(vtln_warp=warp))
+        if utt.speaker:
+            props['speaker'] = utt.speaker
+        props['audio'] = {
+            'file': os.path.abspath(utt.audio_file),
+            'sample_rate': manager.audio_metadata[utt.audio_file].sample_rate}
+        if utt.tstart is not None:
+            props['audio']['tstart'] = utt.tstart
+            props['audio']['tstop'] = utt.tstop
+        props['audio']['duration'] = utt.duration
+        carrier = _Carrier(props, proc.ndims)
+        if cmvn_mode is not None:
+            cmvn = manager.get_cmvn_processor()
+            cmvn.add_stats(stats)
+            carrier = _Carrier(cmvn.get_properties(carrier), proc.ndims)
+        if delta is not None:
+            carrier = _Carrier(delta.get_properties(carrier),
+                               proc.ndims * (delta.order + 1))
+        props = carrier.properties
+        if pitch is not None:
+            pprops = pitch[1].get_properties(
+                _Carrier(pitch[0].get_properties(), 2))
+            props.update(
+                {k: v for k, v in pprops.items() if k != 'pipeline'})
+            for entry in pprops['pipeline']:
+                entry['columns'] = [
+                    c + carrier.ndims for c in entry['columns']]
+                props['pipeline'].append(entry)
+        return props
 
 
 def _check_environment(njobs, log=get_logger('pipeline', 'warning')):

@@ -73,14 +73,28 @@ class FeaturesProcessor(BaseProcessor, metaclass=abc.ABCMeta):
                 raise ValueError(
                     f'utterances and "{key}" have different names')
         utts = [utterances[n] for n in names]
-        if njobs > 1 and len(utts) > 1:
-            with concurrent.futures.ThreadPoolExecutor(njobs) as pool:
-                audios = list(pool.map(lambda u: u.load_audio(), utts))
-        else:
-            audios = [u.load_audio() for u in utts]
-        feats = self._process_batch(
-            audios, **{k: [v[n] for n in names] for k, v in kwargs.items()})
-        return FeaturesCollection(zip(names, feats))
+        listed = {k: [v[n] for n in names] for k, v in kwargs.items()}
+        feats = self._process_stream(utts, njobs, **listed)
+        if feats is None:
+            # bounded batches: neither the audio nor the device buffers of
+            # the whole corpus are alive at once
+            feats, step = [], 256
+            for b in range(0, len(utts), step):
+                part = utts[b:b + step]
+                if njobs > 1 and len(part) > 1:
+                    with concurrent.futures.ThreadPoolExecutor(njobs) as pool:
+                        audios = list(pool.map(lambda u: u.load_audio(), part))
+                else:
+                    audios = [u.load_audio() for u in part]
+                feats += self._process_batch(
+                    audios, **{k: v[b:b + step] for k, v in listed.items()})
+        return FeaturesCollection(
+            (n, f) for n, f in zip(names, feats) if f is not None)
+
+    def _process_stream(self, utts, njobs, **kwargs):
+        """Streamed extraction of a list of Utterance (frame-based processors
+        override it); None when the processor has no streamed path"""
+        return None
 
 
 class FeaturesPostProcessor(FeaturesProcessor):
@@ -220,6 +234,49 @@ class FramesProcessor(FeaturesProcessor, metaclass=abc.ABCMeta):
         return [host[offs[i]:offs[i + 1]] for i in range(len(signals))]
 
 
+def stream_features(processor, utts, njobs, warps=None, with_warp=True):
+    """process_all of a frame-based processor: the utterances are streamed
+    through the fused launch in chunks (shennong_b200.stream), sharded over
+    the ranks of torch.distributed when initialised (every rank returns the
+    whole collection).  None when a signal is not int16 (float audio goes
+    through the per-utterance API, which reproduces the reference's cast)."""
+    from shennong_b200 import stream
+    from shennong_b200.fused import FusedPipeline
+    items, lengths, int16 = stream.audio_items(
+        utts, sample_rate=processor.sample_rate)
+    if not int16:
+        return None
+    warp_of = warps
+    if warps is not None:
+        warps = np.asarray(warps, dtype=np.float32)
+    data, parts = stream.extract_corpus(
+        FusedPipeline(processor), items, lengths, warps=warps, njobs=njobs)
+    feats = [None] * len(utts)
+    for index, plan, row0, _, _ in parts:
+        for j, i in enumerate(index):
+            a = row0 + int(plan.foffs[j])
+            block = data[a:a + int(plan.valid[j])]
+            kwargs = ({'vtln_warp': warp_of[i] if warp_of is not None
+                       else 1.0} if with_warp else {})
+            feats[i] = Features._deferred(
+                block, _Deferred(processor.times, block.shape[0]),
+                _Deferred(processor.get_properties, **kwargs))
+    return feats
+
+
+class _Deferred:
+    """a call made at first access (timestamps / properties of the Features
+    of a batch: tens of thousands of utterances are wrapped without building
+    them up front)"""
+    __slots__ = ('fun', 'args', 'kwargs')
+
+    def __init__(self, fun, *args, **kwargs):
+        self.fun, self.args, self.kwargs = fun, args, kwargs
+
+    def __call__(self):
+        return self.fun(*self.args, **self.kwargs)
+
+
 class MelFeaturesProcessor(FramesProcessor):
     """Base class of the mel-based processors (filterbank, MFCC, PLP)"""
     num_bins = Option(
@@ -281,3 +338,6 @@ class MelFeaturesProcessor(FramesProcessor):
         warps = vtln_warp if vtln_warp is not None else [1.0] * len(audios)
         datas = self._extract(audios, warps)
         return [self._features(d, w) for d, w in zip(datas, warps)]
+
+    def _process_stream(self, utts, njobs, vtln_warp=None):
+        return stream_features(self, utts, njobs, warps=vtln_warp)

@@ -7,7 +7,7 @@ log-energy, ``ndims = padded_window_size / 2 + 1``.
 from shennong_b200 import _lib
 from shennong_b200.base import Option, f32_py
 from shennong_b200.features import Features
-from shennong_b200.processor.base import FramesProcessor
+from shennong_b200.processor.base import FramesProcessor, stream_features
 
 
 class SpectrogramProcessor(FramesProcessor):
@@ -61,3 +61,6 @@ class SpectrogramProcessor(FramesProcessor):
 
     def _process_batch(self, audios):
         return [self._wrap(d) for d in self._extract(audios)]
+
+    def _process_stream(self, utts, njobs):
+        return stream_features(self, utts, njobs, with_warp=False)
