@@ -85,7 +85,11 @@ def parse_args():
                     help='utterances per chunk of the host pipeline (e2e)')
     ap.add_argument('--gather-chunks', type=int, default=8,
                     help='chunks of the device-resident step for N > 1')
-    ap.add_argument('--gather', default='nccl', choices=['nccl', 'none'])
+    ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl', 'none'],
+                    help='collection inside the step for N > 1: libsnb kernel '
+                    'storing into the peers\' buffers over NVLink (p2p), '
+                    'NCCL all-gather (nccl)')
+    ap.add_argument('--gather-ctas', type=int, default=32)
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
 
@@ -488,12 +492,29 @@ def main():
                       device='cuda')
     base = (None if pipe.simple else torch.empty(
         (total_frames, pipe.base_dim), dtype=torch.float32, device='cuda'))
-    gathered, s_comm = None, None
+    gathered, s_comm, peers = None, None, None
     if world > 1 and args.gather != 'none':
-        gathered = [torch.empty((world * c['rows'], pipe.out_dim),
-                                dtype=torch.float32, device='cuda')
-                    for c in chunks]
         s_comm = torch.cuda.Stream()
+        sizes = [world * c['rows'] * pipe.out_dim for c in chunks]
+        bases = np.concatenate(([0], np.cumsum(sizes)))
+        if args.gather == 'p2p':
+            from shennong_b200.distributed import PeerGather
+            peers = PeerGather(int(bases[-1]))
+            flat = peers.tensor
+        else:
+            flat = torch.empty(int(bases[-1]), dtype=torch.float32,
+                               device='cuda')
+        # chunk k of the result: [world, rows_k, D], rank-major
+        gathered = [flat[int(bases[k]):int(bases[k + 1])].view(
+            world * c['rows'], pipe.out_dim) for k, c in enumerate(chunks)]
+
+    def collect(k, c, r0, r1):
+        """rows of chunk k -> every rank (queued on the current stream)"""
+        if peers is not None:
+            peers.push(out[r0:r1], int(bases[k]) + rank * c['rows']
+                       * pipe.out_dim, ctas=args.gather_ctas)
+        else:
+            dist.all_gather_into_tensor(gathered[k], out[r0:r1])
 
     ev_feat = []
 
@@ -517,8 +538,11 @@ def main():
                 done.record(cur)
                 with torch.cuda.stream(s_comm):
                     s_comm.wait_event(done)
-                    dist.all_gather_into_tensor(gathered[k], out[r0:r1])
+                    collect(k, c, r0, r1)
         if gathered is not None:
+            if peers is not None:
+                with torch.cuda.stream(s_comm):
+                    peers.arrive()
             cur.wait_stream(s_comm)      # the step ends with the collection
 
     for w in range(args.warmup):
@@ -560,8 +584,9 @@ def main():
         g0.record()
         for _ in range(3):
             for k, c in enumerate(chunks):
-                dist.all_gather_into_tensor(
-                    gathered[k], out[c['row0']:c['row0'] + c['rows']])
+                collect(k, c, c['row0'], c['row0'] + c['rows'])
+            if peers is not None:
+                peers.arrive()
         g1.record()
         barrier()
         gt = torch.tensor([g0.elapsed_time(g1) / 3], device='cuda',
@@ -572,10 +597,30 @@ def main():
                   'alone_ms': float(gt[0]), 'bytes_per_rank': nbytes,
                   'recv_gbs_per_rank':
                   (world - 1) * nbytes / (float(gt[0]) * 1e-3) / 1e9,
-                  'api': 'all_gather_into_tensor of every chunk of the step '
-                         'on a second stream (NCCL over NVLink), chunk k '
-                         'travels while chunk k + 1 is computed; `alone_ms` '
-                         'is the same collection without compute'}
+                  'how': args.gather,
+                  'api': ('distributed.PeerGather: one libsnb kernel per '
+                          'chunk stores its rows into the result buffers of '
+                          'all ranks (CUDA IPC peer memory over NVLink), a '
+                          '4-byte all-reduce closes the step'
+                          if peers is not None else
+                          'all_gather_into_tensor of every chunk (NCCL over '
+                          'NVLink)') + '; on a second stream, chunk k travels '
+                         'while chunk k + 1 is computed; `alone_ms` is the '
+                         'same collection without compute'}
+        # the gathered result of the last step against the local rows
+        mine = torch.cat([g.view(world, -1, pipe.out_dim)[rank]
+                          for g in gathered])
+        gather['own_rows_intact'] = bool(torch.equal(mine, out))
+        # and every other rank's rows: float64 checksums of the blocks
+        sums = torch.zeros(world, dtype=torch.float64, device='cuda')
+        sums[rank] = out.double().sum()
+        dist.all_reduce(sums)
+        got = torch.stack([torch.cat([
+            g.view(world, -1, pipe.out_dim)[r] for g in gathered]).double().sum()
+            for r in range(world)])
+        okay = torch.tensor([float(torch.equal(got, sums))], device='cuda')
+        dist.all_reduce(okay, op=dist.ReduceOp.MIN)
+        gather['rows_of_all_ranks_match_checksums'] = bool(okay.item() == 1.0)
 
     # ---- parity check on rows of every rank (dither 0, outside the clock) ---
     check = parity_check(args, pipe, info, pcm_dev, host_head, rank, world,
@@ -868,6 +913,33 @@ def api_leg(args, info, rank, world, barrier, torch, dist):
           lambda: proc.process_all(utts, njobs=cores), 13)
     timed('pipeline.extract_features (mfcc + cmvn by speaker with vad + delta)',
           lambda: pipeline.extract_features(config, utts, njobs=cores), 39)
+    # floor of anything that starts from files: the bytes of this rank's
+    # share read from the page cache into pinned memory, nothing else
+    from shennong_b200 import stream
+    from shennong_b200.distributed import shard_utterances
+    ulist = [utts[k] for k in utts.by_name().keys()]
+    items, lengths, _ = stream.audio_items(ulist)
+    mine = shard_utterances(lengths, world)[rank]
+    source = stream.AudioSource([items[i] for i in mine], lengths[mine],
+                                workers=cores)
+    step = 512
+    staging = torch.empty(source.span(0, min(step, len(mine))),
+                          dtype=torch.int16, pin_memory=True)
+    for rep in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        for b in range(0, len(mine), step):
+            source.window(b, min(b + step, len(mine)), staging)
+        barrier()
+        dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    results['read_floor'] = {
+        'ms': float(tt[0]) * 1e3,
+        'gbs_per_rank': float(lengths[mine].sum()) * 2 / float(tt[0]) / 1e9,
+        'what': 'readinto of the same WAV payloads into pinned staging by '
+                f'{cores} threads, no GPU work'}
     results['note'] = (
         f'{n} WAV files of 10 s read from {tempfile.gettempdir()} inside the '
         'timed call (mono 16-bit PCM payloads go straight into pinned '

@@ -104,6 +104,8 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
+// hash32 is a bijection: the keys of the first 2^32 frames of a batch are all
+// different (no birthday collisions between frames)
 __device__ __forceinline__ uint32_t frame_noise_key(uint64_t seed, uint64_t frame) {
   const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
   return hash32(hash32(static_cast<uint32_t>(frame) ^ lo) + static_cast<uint32_t>(frame >> 32)) ^ hi;
@@ -118,7 +120,10 @@ __device__ __forceinline__ uint32_t frame_noise_key(uint64_t seed, uint64_t fram
 // so the .ftz approximations are used as they are (the generic logf / rsqrtf
 // expansions spend 7 instructions on denormal fix-ups).
 __device__ __forceinline__ float2 dither_pair(uint32_t key, uint32_t pair, float c) {
-  const uint32_t h = hash32(key + pair * 0x9e3779b9u);
+  // (xor, not add: with key + pair * G two frames whose keys differ by m * G
+  // would share their whole sequence shifted by m pairs -- likely among 1e7
+  // frames; with xor only isolated samples can coincide)
+  const uint32_t h = hash32(key ^ (pair * 0x9e3779b9u));
   const float u1 = __uint_as_float(0x3f800040u | ((h >> 9) & 0x007fff80u)) - 1.0f;   // (0, 1)
   float l, r, sn, cs;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));

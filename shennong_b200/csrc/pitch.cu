@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(256) pitch_ballast_kernel(const BallastArgs a)
 // 4: rows are 16-byte aligned for the tracker's cp.async), pov [group_frames, nm].
 // ---------------------------------------------------------------------------
 constexpr int kNccfTask = 8;
+constexpr int kNccfWarps = 12;          // per CTA, two CTAs per SM (80 registers)
 
 struct NccfArgs {
   const float *down;
@@ -425,7 +426,7 @@ __host__ __device__ inline NccfSmem nccf_smem_layout(int full_len, int nm, int n
   int off = 0;
   s.z = off; off += (full_len + 6 + 1) & ~1;      // zero tail read by the sliding NCCF loop
   s.pre = off; off += (full_len + 2 + 1) & ~1;
-  s.np = off; off += (nm + nw + 1 + 1) & ~1;      // zero tail for the padded taps
+  s.np = off; off += 2 * ((nm + nw + 1 + 1) & ~1);   // two frames; zero tails for the padded taps
   s.total = off;
   return s;
 }
@@ -437,7 +438,7 @@ __host__ __device__ inline int nccf_shared_words(int ns, int nwp, bool table) {
 // defaults) and the tap table in shared memory; 0: any tap count, table in
 // shared memory when it fits, else read through L1
 template <int NWC>
-__global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
+__global__ void __launch_bounds__(kNccfWarps * 32, 2) pitch_nccf_kernel(const NccfArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarp_cta = blockDim.x >> 5;
@@ -460,9 +461,10 @@ __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
   const NccfSmem L = nccf_smem_layout(fl, nm, nw);
   double *wbase = reinterpret_cast<double *>(smem_raw + 4 * static_cast<size_t>(nccf_shared_words(ns, nwp, table))) +
                   static_cast<size_t>(warp) * L.total;
-  double *w_z = wbase + L.z, *w_pre = wbase + L.pre, *w_np = wbase + L.np;
+  double *w_z = wbase + L.z, *w_pre = wbase + L.pre, *w_np0 = wbase + L.np;
+  const int np_stride = (nm + nw + 1 + 1) & ~1;
   for (int i = fl + lane; i < fl + 6; i += 32) w_z[i] = 0.0;
-  for (int i = nm + lane; i < nm + nw + 1; i += 32) w_np[i] = 0.0;
+  for (int i = nm + lane; i < nm + nw + 1; i += 32) { w_np0[i] = 0.0; w_np0[np_stride + i] = 0.0; }
 
   const int64_t ntasks = (a.q1 - a.q0 + kNccfTask - 1) / kNccfTask;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * nwarp_cta + warp;
@@ -486,7 +488,15 @@ __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
     }
     int64_t kcur = -1, doff = 0, m1 = 0, m2 = 0, end1 = 0, fbase = 0;
     float ballast1 = 0.0f, ballast2 = 0.0f;
-    for (int64_t q = qa; q < qb; ++q) {
+    // two frames per pass: their NCCF rows are upsampled together (one load of
+    // every tap weight for both)
+#pragma unroll 1
+    for (int64_t q2 = qa; q2 < qb; q2 += 2) {
+     const int npass = q2 + 1 < qb ? 2 : 1;
+#pragma unroll 1
+     for (int sub = 0; sub < npass; ++sub) {
+      const int64_t q = q2 + sub;
+      double *w_np = w_np0 + sub * np_stride;
       while (a.gfo[k + 1] <= q) ++k;
       if (k != kcur) {
         kcur = k;
@@ -601,31 +611,45 @@ __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
           }
         }
       }
+     }
       __syncwarp();
       // ---- upsample to the log-spaced lags (taps padded with zero weights to nw); local cost ----
-      float *crow = a.cost + qrel * a.ns4 + lane;
+      const int64_t qrel2 = q2 - a.q0;
+      float *crow = a.cost + qrel2 * a.ns4 + lane;
+      const bool two = npass == 2;
 #pragma unroll 2
       for (int i = lane; i < ns; i += 32, crow += 32) {
-        const double *src = w_np + s_upfirst[i];
-        double acc = 0.0;
+        const double *src = w_np0 + s_upfirst[i];
+        double acc0 = 0.0, acc1 = 0.0;
         if (NWC > 0) {
           const double *w = s_upw + i * nwp;
 #pragma unroll
-          for (int j = 0; j < NWC; ++j) acc = fma(w[j], src[j], acc);
+          for (int j = 0; j < NWC; ++j) {
+            const double wj = w[j];
+            acc0 = fma(wj, src[j], acc0);
+            acc1 = fma(wj, src[np_stride + j], acc1);
+          }
         } else if (table) {
           const double *w = s_upw + i * nwp;
 #pragma unroll 2
-          for (int j = 0; j < nw; ++j) acc = fma(w[j], src[j], acc);
+          for (int j = 0; j < nw; ++j) {
+            acc0 = fma(w[j], src[j], acc0);
+            acc1 = fma(w[j], src[np_stride + j], acc1);
+          }
         } else {
           const double *w = a.up_w_t + static_cast<int64_t>(i) * nwp;
 #pragma unroll 2
-          for (int j = 0; j < nw; ++j) acc = fma(__ldg(w + j), src[j], acc);
+          for (int j = 0; j < nw; ++j) {
+            const double wj = __ldg(w + j);
+            acc0 = fma(wj, src[j], acc0);
+            acc1 = fma(wj, src[np_stride + j], acc1);
+          }
         }
-        const float nccf = static_cast<float>(acc);
         // local_cost = 1 - nccf; local_cost += soft_min_f0 * lag * nccf
-        float c = __fadd_rn(1.0f, -nccf);
-        c = __fadd_rn(__fmul_rn(s_lagc[i], nccf), c);
-        *crow = c;
+        const float lagc = s_lagc[i];
+        const float n0 = static_cast<float>(acc0), n1 = static_cast<float>(acc1);
+        crow[0] = __fadd_rn(__fmul_rn(lagc, n0), __fadd_rn(1.0f, -n0));
+        if (two) crow[a.ns4] = __fadd_rn(__fmul_rn(lagc, n1), __fadd_rn(1.0f, -n1));
       }
     }
   }
@@ -647,13 +671,20 @@ __global__ void __launch_bounds__(512, 2) pitch_nccf_kernel(const NccfArgs a) {
 //   * levels s = kA1/2 ... 1: lane per state i = s(2k+1), serial scan of
 //     [bp(i-s), bp(i+s)] -- 1-3 candidates on the plateaus of bp, 2s+1 where bp
 //     follows i; the few states that straddle a jump of bp (range > 2s+2) are
-//     handed to whole-warp scans instead of stalling their round.
+//     handed to whole-warp scans instead of stalling their round.  (Four such
+//     states at a time, one per group of 8 lanes with a 64-bit (cost, j) key,
+//     was tried: 9 ms slower per 10 000 utterances, most rounds have one or two.)
 // Every scan keeps the first minimum of its range, exactly like the
 // brute-force step (and like Kaldi's bound-tightening search, which the oracle
 // restates: checked equal on 834 000 states in round 1).
 // ---------------------------------------------------------------------------
+// One CTA per SM, up to 28 warps.  (Two CTAs of 17 warps with int16
+// backpointers in shared memory -- 34 utterances in flight per SM, two rounds
+// instead of three for 10 000 utterances -- measured slower per frame: 7.0
+// against 5.9 ns, profiles/r02_pitch_variants.txt.)
 constexpr int kTrackWarpsMax = 28;
 constexpr int kTrackWarpsMin = 4;
+constexpr int kTrackCtasPerSm = 1;
 #ifndef SNB_PITCH_A1LOG2
 #define SNB_PITCH_A1LOG2 6
 #endif
@@ -723,7 +754,7 @@ __device__ __forceinline__ void prefetch_row(float *dst, const float *src, int n
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_viterbi_kernel(const TrackArgs a) {
+__global__ void __launch_bounds__(kTrackWarpsMax * 32, kTrackCtasPerSm) pitch_viterbi_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarp_cta = blockDim.x >> 5;
@@ -736,7 +767,7 @@ __global__ void __launch_bounds__(kTrackWarpsMax * 32, 1) pitch_viterbi_kernel(c
   float *wbase = reinterpret_cast<float *>(smem_raw) + track_shared_words(ns) +
                  static_cast<size_t>(warp) * track_warp_words(ns4, ns);
   float *buf0 = wbase, *buf1 = wbase + ns4, *buf2 = wbase + 2 * ns4;
-  int *w_bp = reinterpret_cast<int *>(wbase + 3 * ns4);
+  int *w_bp = reinterpret_cast<int *>(wbase + 3 * ns4);     // this frame's backpointers
 
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * nwarp_cta + warp;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * nwarp_cta;
@@ -983,7 +1014,7 @@ __global__ void __launch_bounds__(256) process_pitch_kernel(const PostArgs a) {
         int64_t tt = t + j;
         tt = tt < 0 ? 0 : (tt >= F ? F - 1 : tt);
         const float s = __fmul_rn(static_cast<float>(j), inv);
-        if (s != 0.0f) d = fmaf(s, s_logp[tt - lo], d);
+        if (s != 0.0f) d = __fadd_rn(d, __fmul_rn(s, s_logp[tt - lo]));     // (axpy: product, then sum)
       }
       float noise = 0.0f;
       if (o.delta_pitch_noise_stddev != 0.0f) {
@@ -1017,26 +1048,33 @@ static size_t track_smem(const PitchTables *t, int warps) {
           static_cast<size_t>(warps) * track_warp_words(t->ns4, t->nstates)) * 4 + 16;
 }
 
-// most warps (utterances in flight) one CTA of the tracker can hold
+// most warps (utterances in flight) one CTA of the tracker can hold with
+// kTrackCtasPerSm CTAs per SM
 static int track_capacity(const PitchTables *t) {
   static const char *env = getenv("SNB_PITCH_WARPS");          // tuning knob: cap the warps per CTA
   int w = kTrackWarpsMax;
   if (env && atoi(env) >= kTrackWarpsMin) w = std::min(w, atoi(env));
-  while (w > 0 && track_smem(t, w) > kSmemBudget) --w;
+  while (w > 0 && track_smem(t, w) > kSmemBudget / kTrackCtasPerSm) --w;
   return w;
 }
 
-// Tracker launch shape for `nutts` utterances: one CTA per SM; the number of
-// warps per CTA balances the waves (10 000 utterances on 148 SMs x 28 warps
-// would run 2.4 waves = 3 rounds: 23 warps give 3 full ones).  Returns the
-// number of concurrently tracked utterances ("slots" of backpointer scratch).
+// Tracker launch shape for `nutts` utterances: kTrackCtasPerSm CTAs per SM;
+// the number of warps per CTA balances the waves (10 000 utterances on 148
+// SMs x 34 warps run two rounds of 5 000).  Returns the number of concurrently
+// tracked utterances ("slots" of backpointer scratch).
 static int64_t track_shape(const PitchTables *t, int64_t nutts, int *grid_out, int *warps_out) {
-  const int sms = sm_count(), cap = track_capacity(t);
+  const int cap = track_capacity(t);
+  const int64_t ctas = static_cast<int64_t>(sm_count()) * kTrackCtasPerSm;
   const int64_t n = std::max<int64_t>(nutts, 1);
-  const int64_t waves = (n + static_cast<int64_t>(sms) * cap - 1) / (static_cast<int64_t>(sms) * cap);
-  int64_t w = (n + waves * sms - 1) / (waves * sms);
+  if (cap < 1) {
+    if (grid_out) *grid_out = 0;
+    if (warps_out) *warps_out = 0;
+    return 0;
+  }
+  const int64_t waves = (n + ctas * cap - 1) / (ctas * cap);
+  const int64_t w = (n + waves * ctas - 1) / (waves * ctas);
   const int warps = static_cast<int>(std::max<int64_t>(std::min<int64_t>(kTrackWarpsMin, cap), std::min<int64_t>(w, cap)));
-  const int grid = static_cast<int>(std::min<int64_t>((n + warps - 1) / warps, sms));
+  const int grid = static_cast<int>(std::min<int64_t>((n + warps - 1) / warps, ctas));
   if (grid_out) *grid_out = grid;
   if (warps_out) *warps_out = warps;
   return static_cast<int64_t>(grid) * warps;
@@ -1047,7 +1085,7 @@ static NccfShape nccf_shape(const PitchTables *t) {
   NccfShape s;
   const NccfSmem L = nccf_smem_layout(t->full_len, t->nmeas, t->up_nw_max);
   s.table = t->up_nw_max == 10 || static_cast<size_t>(t->nstates) * t->nwp * 8 <= 96 * 1024;
-  s.warps = 16;
+  s.warps = kNccfWarps;
   for (;;) {
     s.smem = static_cast<size_t>(nccf_shared_words(t->nstates, t->nwp, s.table)) * 4 +
              static_cast<size_t>(s.warps) * L.total * 8 + 16;
@@ -1059,31 +1097,42 @@ static NccfShape nccf_shape(const PitchTables *t) {
 
 // Groups of utterances (in sorted order) whose local costs are alive at once.
 // The cost matrix is 4 (ns4 + nm) bytes per frame: a budget of kGroupBytes
-// bounds the scratch whatever the batch; a group is a whole number of tracker
-// waves when it holds several.
+// bounds the scratch whatever the batch.  The batch is cut in equal groups,
+// each one tracker wave when it can be.
 constexpr size_t kGroupBytes = static_cast<size_t>(9) << 30;
 
-static int64_t next_group(const snb_batch *b, const PitchTables *t, int64_t k0, int64_t slots) {
+struct PitchGroups {
+  int64_t per = 0;             // utterances per group
+  int64_t group_frames = 0;    // most frames of a group
+  int64_t max_frames = 0;      // longest utterance
+  int64_t slots = 0;
+  int grid = 0, warps = 0;
+};
+
+static PitchGroups plan_groups(const snb_batch *b, const PitchTables *t) {
+  PitchGroups g;
   const int64_t *gfo = b->down_offsets.data() + 4 * (b->nutts + 1) + b->nutts;
   const size_t per_frame = static_cast<size_t>(t->ns4 + t->nmeas) * 4;
-  const int64_t budget = static_cast<int64_t>(kGroupBytes / per_frame);
-  int64_t k1 = k0 + 1;
-  while (k1 < b->nutts && gfo[k1 + 1] - gfo[k0] <= budget) ++k1;
-  if (k1 - k0 > slots && k1 < b->nutts) k1 = k0 + (k1 - k0) / slots * slots;
-  return k1;
-}
-
-struct PitchScratch { int64_t group_frames = 0, max_frames = 0; };
-static PitchScratch scratch_shape(const snb_batch *b, const PitchTables *t, int64_t slots) {
-  PitchScratch s;
-  const int64_t *gfo = b->down_offsets.data() + 4 * (b->nutts + 1) + b->nutts;
-  for (int64_t k0 = 0; k0 < b->nutts;) {
-    const int64_t k1 = next_group(b, t, k0, slots);
-    s.group_frames = std::max(s.group_frames, gfo[k1] - gfo[k0]);
-    k0 = k1;
+  const int64_t budget = std::max<int64_t>(1, static_cast<int64_t>(kGroupBytes / per_frame));
+  const int64_t total = b->nutts > 0 ? gfo[b->nutts] : 0;
+  int64_t ngroups = std::max<int64_t>(1, (total + budget - 1) / budget);
+  {
+    // ... and one group per tracker wave: 10 000 utterances on 148 x 28 slots
+    // are three groups of 3 334 (23 warps per CTA), not 2.4 waves
+    const int cap = track_capacity(t);
+    const int64_t per_wave = static_cast<int64_t>(sm_count()) * kTrackCtasPerSm * std::max(cap, 1);
+    ngroups = std::max(ngroups, (b->nutts + per_wave - 1) / per_wave);
   }
-  s.max_frames = b->nutts > 0 ? gfo[1] - gfo[0] : 0;     // sorted: the first utterance is the longest
-  return s;
+  for (;;) {                    // (sorted by decreasing length: the first group is the heaviest)
+    g.per = std::max<int64_t>(1, (b->nutts + ngroups - 1) / ngroups);
+    if (g.per == 1 || gfo[std::min(g.per, b->nutts)] <= budget) break;
+    ++ngroups;
+  }
+  for (int64_t k0 = 0; k0 < b->nutts; k0 += g.per)
+    g.group_frames = std::max(g.group_frames, gfo[std::min(k0 + g.per, b->nutts)] - gfo[k0]);
+  g.max_frames = b->nutts > 0 ? gfo[1] - gfo[0] : 0;     // sorted: the first utterance is the longest
+  g.slots = track_shape(t, std::min(g.per, std::max<int64_t>(b->nutts, 1)), &g.grid, &g.warps);
+  return g;
 }
 
 }  // namespace snb
@@ -1125,15 +1174,14 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 extern "C" int64_t snb_pitch_workspace_bytes(const snb_plan *plan, const snb_batch *batch) {
   if (!plan || plan->kind != 1 || !batch) return -1;
   const PitchTables *t = plan->pitch;
-  const int64_t slots = track_shape(t, batch->nutts, nullptr, nullptr);
-  const PitchScratch s = scratch_shape(batch, t, slots);
-  const int64_t mf = std::max<int64_t>(1, s.max_frames);
+  const PitchGroups g = plan_groups(batch, t);
+  const int64_t mf = std::max<int64_t>(1, g.max_frames);
   size_t bytes = align256(static_cast<size_t>(batch->total_down + 8) * 4) + 256;   // + utterance queue
   bytes += align256(static_cast<size_t>(batch->nutts + 1) * 2 * 4);                 // ballast
-  bytes += align256(static_cast<size_t>(s.group_frames + 1) * t->ns4 * 4);          // local costs
-  bytes += align256(static_cast<size_t>(s.group_frames + 1) * t->nmeas * 4);        // POV NCCF
-  bytes += align256(static_cast<size_t>(slots) * mf * t->nstates * 2);              // backpointers
-  bytes += align256(static_cast<size_t>(slots) * mf * 4);                           // state sequences
+  bytes += align256(static_cast<size_t>(g.group_frames + 1) * t->ns4 * 4);          // local costs
+  bytes += align256(static_cast<size_t>(g.group_frames + 1) * t->nmeas * 4);        // POV NCCF
+  bytes += align256(static_cast<size_t>(g.slots) * mf * t->nstates * 2);            // backpointers
+  bytes += align256(static_cast<size_t>(g.slots) * mf * 4);                         // state sequences
   return static_cast<int64_t>(bytes);
 }
 
@@ -1161,11 +1209,11 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   const PitchTables *t = plan->pitch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   batch->note_stream(stream);
-  int grid = 1, warps = kTrackWarpsMin;
-  const int64_t slots = track_shape(t, batch->nutts, &grid, &warps);
+  const PitchGroups pg = plan_groups(batch, t);
+  const int grid = pg.grid, warps = pg.warps;
+  const int64_t slots = pg.slots;
   if (warps < 1) return set_error(SNB_ERR_UNSUPPORTED, "pitch options outside the GPU path limits");
-  const PitchScratch sc = scratch_shape(batch, t, slots);
-  const int64_t mf = std::max<int64_t>(1, sc.max_frames);
+  const int64_t mf = std::max<int64_t>(1, pg.max_frames);
   unsigned char *ws = static_cast<unsigned char *>(d_workspace);
   float *down = reinterpret_cast<float *>(ws);
   ws += align256(static_cast<size_t>(batch->total_down + 8) * 4);
@@ -1174,9 +1222,9 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   float *ballast = reinterpret_cast<float *>(ws);
   ws += align256(static_cast<size_t>(batch->nutts + 1) * 2 * 4);
   float *cost = reinterpret_cast<float *>(ws);
-  ws += align256(static_cast<size_t>(sc.group_frames + 1) * t->ns4 * 4);
+  ws += align256(static_cast<size_t>(pg.group_frames + 1) * t->ns4 * 4);
   float *pov = reinterpret_cast<float *>(ws);
-  ws += align256(static_cast<size_t>(sc.group_frames + 1) * t->nmeas * 4);
+  ws += align256(static_cast<size_t>(pg.group_frames + 1) * t->nmeas * 4);
   int16_t *bp = reinterpret_cast<int16_t *>(ws);
   ws += align256(static_cast<size_t>(slots) * mf * t->nstates * 2);
   int32_t *states = reinterpret_cast<int32_t *>(ws);
@@ -1218,7 +1266,7 @@ extern "C" int snb_compute_pitch(const snb_plan *plan, const snb_batch *batch, c
   const int sms = sm_count();
 
   for (int64_t k0 = 0; k0 < batch->nutts;) {
-    const int64_t k1 = next_group(batch, t, k0, slots);
+    const int64_t k1 = std::min(k0 + pg.per, batch->nutts);
     const int64_t q0 = h_gfo[k0], q1 = h_gfo[k1];
     if (q1 > q0) {
       NccfArgs n;

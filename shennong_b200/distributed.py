@@ -135,6 +135,95 @@ def all_gather_objects(obj, group=None):
     return out
 
 
+class _DeviceBuffer:
+    """CUDA array interface over a raw device pointer (zero-copy tensor)"""
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {
+            'shape': (int(nfloats),), 'typestr': '<f4',
+            'data': (int(ptr), False), 'version': 2}
+
+
+class PeerGather:
+    """Collection by direct stores over NVLink
+
+    Every rank owns a float32 result buffer of `nfloats`; the buffers are
+    mapped in every process of the node through CUDA IPC
+    (``snb_peer_buffer_*``) and :meth:`push` writes a block of finished rows
+    at the same offset of ALL of them with one libsnb kernel
+    (``snb_gather_rows``) on the current stream -- the all-gather of the
+    north star as posted writes, issued by the producer as soon as a chunk is
+    done, with no rendezvous per chunk.  :meth:`arrive` is the one
+    synchronisation of a step: a 4-byte all-reduce queued behind the pushes.
+    """
+
+    def __init__(self, nfloats, group=None):
+        import ctypes
+        import torch
+        from shennong_b200 import _lib
+        dist = _dist()
+        self.rank, self.size = world()
+        self.group = group
+        self.nfloats = int(nfloats)
+        L = _lib.lib()
+        self._lib = L
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(L.snb_peer_buffer_create(
+            self.nfloats * 4, ctypes.byref(ptr), handle))
+        self._own = ptr.value
+        handles = all_gather_objects(bytes(handle), group)
+        self._opened = []
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self._own)
+                continue
+            peer = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _lib.check(L.snb_peer_buffer_open(buf, ctypes.byref(peer)))
+            self._opened.append(peer.value)
+            ptrs.append(peer.value)
+        self._ptrs = (ctypes.c_void_p * self.size)(*ptrs)
+        self.tensor = torch.as_tensor(
+            _DeviceBuffer(self._own, self.nfloats), device='cuda')
+        self._flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        if self.size > 1:
+            dist.barrier(group=group)
+
+    def push(self, src, offset_floats, ctas=32):
+        """`src` (contiguous float32 device tensor, a multiple of 4 elements)
+        -> floats [offset, offset + src.numel()) of every rank's buffer"""
+        import ctypes
+        import torch
+        from shennong_b200 import _lib
+        if not src.is_contiguous():
+            raise ValueError('contiguous rows expected')
+        _lib.check(self._lib.snb_gather_rows(
+            ctypes.c_void_p(src.data_ptr()), src.numel(), self._ptrs,
+            self.size, int(offset_floats), int(ctas),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def arrive(self):
+        """queued on the current stream: completes when every rank's pushes
+        queued before its own arrive() have completed"""
+        if self.size > 1:
+            _dist().all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        import ctypes
+        import torch
+        torch.cuda.synchronize()
+        if self.size > 1:
+            _dist().barrier(group=self.group)
+        for p in self._opened:
+            self._lib.snb_peer_buffer_close(ctypes.c_void_p(p))
+        self._opened = []
+        self.tensor = None
+        if self._own:
+            self._lib.snb_peer_buffer_destroy(ctypes.c_void_p(self._own))
+            self._own = None
+
+
 def allreduce_stats(stats, group=None):
     """Sums float64 CMVN statistics [G, 2, d+1] over the ranks (only needed
     when a speaker is split across GPUs)"""

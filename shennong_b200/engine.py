@@ -395,6 +395,8 @@ def process_pitch(post_opts, raw, layout, seed=0, out=None, out_layout=None):
                 else raw.shape[0] + delay * layout.nutts)
         out = torch.zeros((rows, max(dim, 1)), dtype=torch.float32,
                           device='cuda')
+    if out.shape[0] == 0 or raw.shape[0] == 0:
+        return out          # (pitch frames only where the features have none)
     _lib.check(L.snb_process_pitch(
         _lib.ref(post_opts), _ptr(raw), raw.stride(0), layout.ptr,
         out_layout.ptr if out_layout is not None else None,

@@ -20,6 +20,7 @@ import abc
 import copy
 import json
 import os
+import importlib
 import pickle
 import struct
 
@@ -257,23 +258,80 @@ class NumpySerializer(FeaturesSerializer):
             for k, v in raw.items())
 
 
+class _ModuleRef:
+    """pickles as ``importlib.import_module(name)``"""
+    def __init__(self, name):
+        self.name = name
+
+    def __reduce__(self):
+        return importlib.import_module, (self.name,)
+
+
+class _ReferencePickler(pickle.Pickler):
+    """Pickles the collection OBJECT like the reference does
+    (serializers.py:333-351), with the classes recorded under the reference's
+    module paths (``shennong.features.Features``,
+    ``shennong.features_collection.FeaturesCollection``): the file loads in
+    the reference as its own classes, and here through
+    :class:`_ReferenceUnpickler`.  ``with_properties=False`` drops the
+    properties like the reference's ``_NoPropertiesPickler``."""
+    def __init__(self, stream, with_properties, collection_class):
+        super().__init__(stream, protocol=4)
+        self._with_properties = with_properties
+        self._collection_class = collection_class
+
+    def reducer_override(self, obj):
+        if obj is Features:
+            return getattr, (_ModuleRef('shennong.features'), 'Features')
+        if obj is self._collection_class:
+            return getattr, (_ModuleRef('shennong.features_collection'),
+                             'FeaturesCollection')
+        if isinstance(obj, Features):
+            return Features, (
+                obj.data, obj.times,
+                obj.properties if self._with_properties else None, False)
+        return NotImplemented
+
+
+def _import_reference_module(name):
+    if name == 'shennong' or name.startswith('shennong.'):
+        name = 'shennong_b200' + name[len('shennong'):]
+    return importlib.import_module(name)
+
+
+class _ReferenceUnpickler(pickle.Unpickler):
+    """Resolves the reference's module paths to this package (files written
+    by the reference or by :class:`_ReferencePickler`), without installing
+    the global import alias of shennong_b200.compat"""
+    def find_class(self, module, name):
+        if (module, name) == ('importlib', 'import_module'):
+            return _import_reference_module
+        if module == 'shennong' or module.startswith('shennong.'):
+            module = 'shennong_b200' + module[len('shennong'):]
+        return super().find_class(module, name)
+
+
 class PickleSerializer(FeaturesSerializer):
-    """python pickle '.pkl' format"""
+    """python pickle '.pkl' format: the FeaturesCollection object itself, as
+    the reference writes it (serializers.py:340-351)"""
     def _save(self, features, with_properties):
         self._log.info('writing %s', self.filename)
         with open(self.filename, 'wb') as stream:
-            pickle.dump(self._as_dicts(features, with_properties), stream,
-                        protocol=4)
+            _ReferencePickler(
+                stream, with_properties, type(features)).dump(features)
 
     def _load(self):
         self._log.info('loading %s', self.filename)
         with open(self.filename, 'rb') as stream:
-            raw = pickle.load(stream)
-        if isinstance(raw, self._features_collection):
-            return raw
-        return self._features_collection(
-            (k, Features._from_dict(v, validate=False))
-            for k, v in raw.items())
+            raw = _ReferenceUnpickler(stream).load()
+        if isinstance(raw, dict) and not isinstance(
+                raw, self._features_collection) and all(
+                    isinstance(v, dict) for v in raw.values()):
+            # files written by round 1 of this package: {name: {data, ...}}
+            return self._features_collection(
+                (k, Features._from_dict(v, validate=False))
+                for k, v in raw.items())
+        return raw
 
 
 class MatlabSerializer(FeaturesSerializer):
@@ -289,15 +347,24 @@ class MatlabSerializer(FeaturesSerializer):
         import scipy.io
         self._log.info('loading %s', self.filename)
         raw = scipy.io.loadmat(
-            self.filename, appendmat=False, squeeze_me=True, mat_dtype=True,
+            self.filename, appendmat=False, squeeze_me=True, mat_dtype=False,
             struct_as_record=False)
         features = self._features_collection()
         for key, value in raw.items():
             if key in ('__header__', '__version__', '__globals__'):
                 continue
             entry = self._plain(value)
-            # squeeze_me also squeezes one-frame / one-dimension features
-            data = np.atleast_2d(entry['data'])
+            # squeeze_me also squeezes one-frame / one-dimension features (and
+            # turns a 1 x 1 matrix into a Python scalar, losing its dtype):
+            # those are read again as stored
+            data = entry['data']
+            if np.ndim(data) < 2:
+                stored = scipy.io.loadmat(
+                    self.filename, appendmat=False, squeeze_me=False,
+                    mat_dtype=False, struct_as_record=False,
+                    variable_names=[key])[key][0, 0].data
+                data = np.asarray(data, dtype=stored.dtype)
+            data = np.atleast_2d(data)
             times = np.atleast_1d(entry['times'])
             if data.shape[0] != times.shape[0]:
                 if data.shape[0] == 1 and times.ndim == 1 and (

@@ -380,3 +380,31 @@ def test_unaligned_utterance_offsets():
         for i, sig in enumerate(sigs):
             single = proc.process(Audio(sig, 16000)).data
             assert np.array_equal(out[offs[i]:offs[i + 1]], single), i
+
+
+def test_dither_statistics():
+    """dither = N(0, 1) per sample, independent across samples and frames
+    (Kaldi draws every sample anew): on a silent signal the frame energy is a
+    chi-square with 400 degrees of freedom -- mean 400, variance 800 -- and
+    the energies of different frames are uncorrelated, on the fused fast path
+    (counter-based Box-Muller) as on the generic one"""
+    from shennong_b200.processor import EnergyProcessor
+    silence = Audio(np.zeros(16000 * 200, np.int16), 16000)
+    for kwargs in ({}, {'frame_length': 0.04}):        # fast path, generic path
+        proc = EnergyProcessor(
+            dither=1.0, remove_dc_offset=False, raw_energy=True,
+            compression='off', **kwargs)
+        e = proc.process(silence).data.reshape(-1)
+        dof = int(16000 * proc.frame_length)
+        assert e.shape[0] > 19000
+        assert abs(e.mean() / dof - 1.0) < 0.01
+        assert abs(e.var() / (2 * dof) - 1.0) < 0.1
+        for lag in (1, 2, 3, 7):
+            c = np.corrcoef(e[:-lag], e[lag:])[0, 1]
+            # frames overlap (shift 160 of 400/640 samples): the expected
+            # correlation of the energies is the shared fraction
+            shared = max(0.0, 1.0 - lag * 160 / dof)
+            assert abs(c - shared) < 0.05, (lag, c, shared)
+        # another seed gives other noise
+        e2 = proc.process(silence).data.reshape(-1)
+        assert abs(np.corrcoef(e, e2)[0, 1]) < 0.05

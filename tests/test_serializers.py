@@ -133,3 +133,70 @@ def test_json_numpy_content():
     back = serializers.json_loads(serializers.json_dumps(data))
     assert np.array_equal(back['a'], data['a']) and back['a'].shape == (2, 3)
     assert back['b'] == 1.5 and back['c'] == [1, 'x', {'d': 3}]
+
+
+def test_matlab_keeps_dtype_of_small_matrices(tmp_path):
+    """a 1 x 1 (or one-frame, one-column) float32 matrix comes back float32"""
+    coll = FeaturesCollection(
+        one=Features(np.ones((1, 1), np.float32), np.zeros((1, 2))),
+        row=Features(np.ones((1, 4), np.float32), np.zeros((1, 2))),
+        col=Features(np.ones((3, 1), np.float32), np.zeros((3, 2))),
+        dbl=Features(np.ones((2, 2), np.float64), np.zeros((2, 2))))
+    coll.save(str(tmp_path / 'f.mat'))
+    back = FeaturesCollection.load(str(tmp_path / 'f.mat'))
+    for name, feats in coll.items():
+        assert back[name].dtype == feats.dtype, name
+        assert back[name].shape == feats.shape, name
+    assert back == coll
+
+
+def test_pickle_is_the_reference_format(tmp_path):
+    """the .pkl holds the collection OBJECT under the reference's class
+    paths (shennong/serializers.py:333-351): a process that has the
+    reference package loads it with a plain pickle.load, and files written
+    by the reference load here"""
+    import pickle
+    import subprocess
+    import sys
+    import textwrap
+    coll = FeaturesCollection(
+        a=Features(np.random.rand(5, 3).astype(np.float32),
+                   np.arange(5) * 0.01, {'pipeline': [], 'x': {'y': 1}}),
+        b=Features(np.zeros((2, 3)), np.zeros((2, 2))))
+    path = tmp_path / 'feats.pkl'
+    coll.save(str(path))
+    assert FeaturesCollection.load(str(path)) == coll
+    coll.save(str(tmp_path / 'bare.pkl'), with_properties=False)
+    bare = FeaturesCollection.load(str(tmp_path / 'bare.pkl'))
+    assert bare['a'].properties == {} and np.array_equal(
+        bare['a'].data, coll['a'].data)
+    # a stand-in for the reference package: same module paths, same attribute
+    # names (features.py:62-67), no knowledge of shennong_b200
+    fake = tmp_path / 'fake' / 'shennong'
+    fake.mkdir(parents=True)
+    (fake / '__init__.py').write_text('')
+    (fake / 'features.py').write_text(textwrap.dedent("""
+        class Features:
+            def __init__(self, data, times, properties=None, validate=True):
+                self._data, self._times = data, times
+                self._properties = {} if properties is None else properties
+    """))
+    (fake / 'features_collection.py').write_text(
+        'class FeaturesCollection(dict):\n    pass\n')
+    script = textwrap.dedent(f"""
+        import pickle, sys
+        sys.path.insert(0, {str(tmp_path / 'fake')!r})
+        coll = pickle.load(open({str(path)!r}, 'rb'))
+        assert type(coll).__module__ == 'shennong.features_collection'
+        assert type(coll['a']).__module__ == 'shennong.features'
+        assert coll['a']._data.shape == (5, 3) and coll['a']._properties['x'] == dict(y=1)
+        assert 'shennong_b200' not in sys.modules
+        pickle.dump(coll, open({str(tmp_path / 'ref.pkl')!r}, 'wb'))
+        print('ok')
+    """)
+    out = subprocess.run([sys.executable, '-c', script], capture_output=True,
+                         text=True)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr
+    # ... and what the "reference" wrote loads here as this package's classes
+    back = FeaturesCollection.load(str(tmp_path / 'ref.pkl'))
+    assert type(back) is FeaturesCollection and back == coll
