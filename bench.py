@@ -81,15 +81,20 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-api', action='store_true')
     ap.add_argument('--api-utts', type=int, default=2000)
-    ap.add_argument('--chunk-utts', type=int, default=512,
-                    help='utterances per chunk of the host pipeline (e2e)')
+    ap.add_argument('--chunk-utts', type=int, default=0,
+                    help='utterances per chunk of the host pipeline (e2e); '
+                    '0: the runner\'s default (512, or one round of the '
+                    'pitch tracker when the pipeline has pitch)')
     ap.add_argument('--gather-chunks', type=int, default=8,
                     help='chunks of the device-resident step for N > 1')
     ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl', 'none'],
                     help='collection inside the step for N > 1: libsnb kernel '
                     'storing into the peers\' buffers over NVLink (p2p), '
                     'NCCL all-gather (nccl)')
-    ap.add_argument('--gather-ctas', type=int, default=32)
+    ap.add_argument('--gather-ctas', type=int, default=64)
+    ap.add_argument('--force-chunks', action='store_true',
+                    help='cut the step in --gather-chunks chunks even without '
+                    'collection (diagnosis of the chunking cost)')
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
 
@@ -471,8 +476,13 @@ def main():
 
     # ---- chunks of the device-resident step (one chunk when N = 1) ---------
     nchunks = 1
-    if world > 1 and args.gather != 'none':
+    if (world > 1 and args.gather != 'none') or args.force_chunks:
         nchunks = max(1, min(args.gather_chunks, nutts // UTTS_PER_SPEAKER))
+        if pipe.pitch is not None:
+            # the pitch tracker follows one utterance per warp: a chunk must
+            # fill a round of it (4 736 utterances) or the kernel runs empty
+            wave = int(L.snb_pitch_wave_utts(plans['pitch'].handle))
+            nchunks = max(1, min(nchunks, -(-nutts // wave)))
     per = -(-nutts // nchunks)
     per = -(-per // UTTS_PER_SPEAKER) * UTTS_PER_SPEAKER     # whole speakers
     bounds = [(b, min(b + per, nutts)) for b in range(0, nutts, per)]
@@ -836,14 +846,14 @@ def end_to_end(args, pipe, pcm_dev, out, starts, lengths, speakers,
     nrep = max(2, min(args.steps, 5))
     for _ in range(2):                                           # warm-up
         pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
-                      chunk_utts=args.chunk_utts, speakers=spk)
+                      chunk_utts=args.chunk_utts or None, speakers=spk)
     barrier()
     rep_ms = []
     t_e0 = time.perf_counter()
     for _ in range(nrep):
         t_r = time.perf_counter()
         pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
-                      chunk_utts=args.chunk_utts, speakers=spk)
+                      chunk_utts=args.chunk_utts or None, speakers=spk)
         rep_ms.append((time.perf_counter() - t_r) * 1e3)
     barrier()
     dt = (time.perf_counter() - t_e0) / nrep
@@ -857,8 +867,9 @@ def end_to_end(args, pipe, pcm_dev, out, starts, lengths, speakers,
             'ms_per_step': dt * 1e3,
             'ms_each_step': [round(t, 2) for t in rep_ms],
             'api': 'FusedPipeline.run_host (stream.StreamRunner: chunked '
-                   f'H2D / compute / D2H, {args.chunk_utts} utterances per '
-                   'chunk; every rank returns the rows of its shard)',
+                   f'H2D / compute / D2H, {pipe._runner.chunk_utts} '
+                   'utterances per chunk; every rank returns the rows of its '
+                   'shard)',
             'pcie_h2d_gbs': h2d_gbs, 'pcie_d2h_gbs': d2h_gbs,
             'host_ceiling_ms': both_s * 1e3,
             'fraction_of_host_ceiling': both_s / dt,

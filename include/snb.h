@@ -286,6 +286,9 @@ int snb_convert_f64_to_f32(const double *d_in, float *d_out, int64_t n,
 /* ---- pitch --------------------------------------------------------------- */
 /* frames compute_kaldi_pitch returns for nsamples (pitch_kaldi.py:298) */
 int64_t snb_pitch_num_frames(int64_t nsamples, const snb_pitch_opts *po);
+/* utterances the tracker follows at once (one warp each): batches of a
+ * multiple of it keep every round of the Viterbi kernel full */
+int64_t snb_pitch_wave_utts(const snb_plan *plan);
 /* the same for n utterance lengths at once (HOST arrays): a corpus is planned
  * (row offsets of every utterance) before its first chunk is uploaded */
 void snb_pitch_num_frames_array(const int64_t *nsamples, int64_t n,

@@ -136,6 +136,7 @@ SIGNATURES = {
     'snb_convert_f64_to_f32': (ctypes.c_int, [vp, vp, i64, vp]),
     'snb_pitch_num_frames': (i64, [i64, vp]),
     'snb_pitch_num_frames_array': (None, [vp, i64, vp, vp]),
+    'snb_pitch_wave_utts': (i64, [vp]),
     'snb_pitch_workspace_bytes': (i64, [vp, vp]),
     'snb_compute_pitch': (ctypes.c_int, [vp, vp, vp, vp, i64, vp, i64, vp]),
     'snb_process_pitch_dim': (i32, [vp]),

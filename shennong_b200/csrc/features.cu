@@ -811,17 +811,20 @@ generic_features_kernel(const GenArgs a) {
     __syncwarp();
     // load (reflect at edges), dither
     float lsum = 0.0f;
-    for (int i = lane; i < W; i += 32) {
-      int64_t k = start + i;
-      while (k < 0 || k >= n) k = (k < 0) ? (-k - 1) : (2 * n - 1 - k);
-      float v = a.pcm_f32 ? a.pcm_f32[utt_off + k] : static_cast<float>(a.pcm[utt_off + k]);
-      if (p.fo.dither != 0.0f) {
-        float g0, g1;
-        gauss_pair(a.seed, static_cast<uint64_t>(row), i >> 1, &g0, &g1);
-        v = fmaf(p.fo.dither, (i & 1) ? g1 : g0, v);
+    for (int i0 = 2 * lane; i0 < W; i0 += 64) {          // a lane takes sample PAIRS: one Box-Muller for two
+      float g[2] = {0.0f, 0.0f};
+      if (p.fo.dither != 0.0f) gauss_pair(a.seed, static_cast<uint64_t>(row), i0 >> 1, &g[0], &g[1]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = i0 + e;
+        if (i >= W) break;
+        int64_t k = start + i;
+        while (k < 0 || k >= n) k = (k < 0) ? (-k - 1) : (2 * n - 1 - k);
+        float v = a.pcm_f32 ? a.pcm_f32[utt_off + k] : static_cast<float>(a.pcm[utt_off + k]);
+        if (p.fo.dither != 0.0f) v = fmaf(p.fo.dither, g[e], v);
+        buf_a[i] = v;
+        lsum += v;
       }
-      buf_a[i] = v;
-      lsum += v;
     }
     float mean = 0.0f;
     if (p.fo.remove_dc_offset) mean = __fdiv_rn(group_sum<32>(lsum), static_cast<float>(W));
@@ -851,7 +854,10 @@ generic_features_kernel(const GenArgs a) {
       }
       e_post = fmaf(v, v, e_post);
       e64 += static_cast<double>(v) * v;
-      const int dst = (a.log2n >= 0) ? static_cast<int>(__brev(static_cast<unsigned>(i)) >> (32 - a.log2n)) : i;
+      // (bit-reversed for the small radix-2 transform; natural order for the
+      //  Stockham transform and the direct DFT)
+      const int dst = (a.log2n >= 0 && a.log2n < 4)
+                          ? static_cast<int>(__brev(static_cast<unsigned>(i)) >> (32 - a.log2n)) : i;
       buf_b[dst] = v;
     }
     if (xo.kind == SNB_FEAT_ENERGY) {
@@ -863,7 +869,66 @@ generic_features_kernel(const GenArgs a) {
     if (p.need_post_energy) log_energy = logf(fmaxf(group_sum<32>(e_post), p.eps_energy));
     __syncwarp();
     float *P;
-    if (a.log2n >= 0) {
+    if (a.log2n >= 4) {
+      // Real FFT of N points as ONE complex FFT of M = N/2 points on
+      // z[n] = x[2n] + i x[2n+1] (the float2 view of buf_b), Stockham autosort
+      // (no bit reversal) with radix-4 stages -- one radix-2 stage first when
+      // log2 M is odd -- ping-ponging between the two buffers, then the
+      // split X[k] = E[k] + W_N^k O[k].  N = 256: 3 radix-4 stages + 1 radix-2
+      // of 32 / 64 butterflies, one per lane (the radix-2 transform of the full
+      // complex N-point problem this replaces ran 8 passes of 128).
+      const int M = half, log2m = a.log2n - 1;
+      float2 *zin = reinterpret_cast<float2 *>(buf_b), *zout = reinterpret_cast<float2 *>(buf_a);
+      const float2 *tw = p.t.tw_dft;                       // exp(-2 pi i k / N), k < N
+      int Ns = 1;
+      if (log2m & 1) {
+        for (int j = lane; j < M / 2; j += 32) {
+          const float2 u = zin[j], v = zin[j + M / 2];
+          zout[2 * j] = make_float2(u.x + v.x, u.y + v.y);
+          zout[2 * j + 1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncwarp();
+        float2 *t = zin; zin = zout; zout = t;
+        Ns = 2;
+      }
+      for (; Ns < M; Ns <<= 2) {
+        const int tstep = 2 * (M / (Ns * 4));              // W_M^(k M / 4 Ns) = tw[2 k M / 4 Ns]
+        const int q = M / 4;
+        for (int j = lane; j < q; j += 32) {
+          const int k = j & (Ns - 1);
+          float2 v0 = zin[j], v1 = zin[j + q], v2 = zin[j + 2 * q], v3 = zin[j + 3 * q];
+          if (Ns > 1) {
+            const float2 w1 = __ldg(tw + k * tstep), w2 = __ldg(tw + 2 * k * tstep),
+                         w3 = __ldg(tw + 3 * k * tstep);
+            v1 = make_float2(v1.x * w1.x - v1.y * w1.y, v1.x * w1.y + v1.y * w1.x);
+            v2 = make_float2(v2.x * w2.x - v2.y * w2.y, v2.x * w2.y + v2.y * w2.x);
+            v3 = make_float2(v3.x * w3.x - v3.y * w3.y, v3.x * w3.y + v3.y * w3.x);
+          }
+          const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+          const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+          const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);          // -i (v1 - v3)
+          const int j0 = ((j - k) << 2) + k;
+          zout[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+          zout[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+          zout[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+          zout[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+        }
+        __syncwarp();
+        float2 *t = zin; zin = zout; zout = t;
+      }
+      // split + power spectrum into the other buffer
+      float *pw = reinterpret_cast<float *>(zout);
+      for (int k = lane; k <= M; k += 32) {
+        const float2 zk = zin[k & (M - 1)], zm = zin[(M - k) & (M - 1)];
+        const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);     // E = (Z[k] + conj Z[M-k]) / 2
+        const float dr = zk.x - zm.x, di = zk.y + zm.y;                       // D = Z[k] - conj Z[M-k]
+        const float orr = 0.5f * di, oi = -0.5f * dr;                         // O = -i D / 2
+        const float2 w = __ldg(tw + k);
+        const float xr = er + (orr * w.x - oi * w.y), xi = ei + (orr * w.y + oi * w.x);
+        pw[k] = (k == 0 || k == M) ? xr * xr : xr * xr + xi * xi;
+      }
+      P = pw;
+    } else if (a.log2n >= 0) {
       // in-place radix-2 DIT: real part buf_b, imaginary part buf_a
       for (int i = lane; i < N; i += 32) buf_a[i] = 0.0f;
       __syncwarp();

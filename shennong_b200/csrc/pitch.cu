@@ -678,11 +678,11 @@ __global__ void __launch_bounds__(kNccfWarps * 32, 2) pitch_nccf_kernel(const Nc
 // brute-force step (and like Kaldi's bound-tightening search, which the oracle
 // restates: checked equal on 834 000 states in round 1).
 // ---------------------------------------------------------------------------
-// One CTA per SM, up to 28 warps.  (Two CTAs of 17 warps with int16
+// One CTA per SM, up to 32 warps (4 736 utterances in flight).  (Two CTAs of 17 warps with int16
 // backpointers in shared memory -- 34 utterances in flight per SM, two rounds
 // instead of three for 10 000 utterances -- measured slower per frame: 7.0
 // against 5.9 ns, profiles/r02_pitch_variants.txt.)
-constexpr int kTrackWarpsMax = 28;
+constexpr int kTrackWarpsMax = 32;
 constexpr int kTrackWarpsMin = 4;
 constexpr int kTrackCtasPerSm = 1;
 #ifndef SNB_PITCH_A1LOG2
@@ -1117,8 +1117,8 @@ static PitchGroups plan_groups(const snb_batch *b, const PitchTables *t) {
   const int64_t total = b->nutts > 0 ? gfo[b->nutts] : 0;
   int64_t ngroups = std::max<int64_t>(1, (total + budget - 1) / budget);
   {
-    // ... and one group per tracker wave: 10 000 utterances on 148 x 28 slots
-    // are three groups of 3 334 (23 warps per CTA), not 2.4 waves
+    // ... and one group per tracker wave: 10 000 utterances on 148 x 32 slots
+    // are three groups of 3 334 (23 warps per CTA), not 2.1 waves
     const int cap = track_capacity(t);
     const int64_t per_wave = static_cast<int64_t>(sm_count()) * kTrackCtasPerSm * std::max(cap, 1);
     ngroups = std::max(ngroups, (b->nutts + per_wave - 1) / per_wave);
@@ -1149,6 +1149,11 @@ extern "C" int64_t snb_pitch_num_frames(int64_t nsamples, const snb_pitch_opts *
 extern "C" void snb_pitch_num_frames_array(const int64_t *nsamples, int64_t n, const snb_pitch_opts *po,
                                            int64_t *out) {
   for (int64_t i = 0; i < n; ++i) out[i] = snb_pitch_num_frames(nsamples[i], po);
+}
+
+extern "C" int64_t snb_pitch_wave_utts(const snb_plan *plan) {
+  if (!plan || plan->kind != 1) return 0;
+  return static_cast<int64_t>(sm_count()) * kTrackCtasPerSm * std::max(track_capacity(plan->pitch), 1);
 }
 
 extern "C" int snb_pitch_plan_create(const snb_pitch_opts *po, snb_plan **out) {

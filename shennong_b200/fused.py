@@ -232,7 +232,7 @@ class FusedPipeline:
         return out, batch.frame_offsets, stats, group
 
     # -- end-to-end: pinned host PCM in, pinned host features out ------------
-    def run_host(self, host_pcm, starts, lengths, chunk_utts=512,
+    def run_host(self, host_pcm, starts, lengths, chunk_utts=None,
                  out_host=None, speakers=None):
         """Streams chunks of a packed pinned PCM buffer through the pipeline
         (H2D / compute / D2H on three streams, :mod:`shennong_b200.stream`)
@@ -242,7 +242,8 @@ class FusedPipeline:
         Returns (pinned float32 [total_frames, out_dim], frame_offsets).
         """
         from shennong_b200 import stream
-        if self._runner is None or self._runner.chunk_utts != chunk_utts:
+        if self._runner is None or (
+                chunk_utts and self._runner.chunk_utts != chunk_utts):
             self._runner = stream.StreamRunner(self, chunk_utts=chunk_utts)
         source = stream.PackedSource(host_pcm, starts, lengths)
         out, plan, stats = self._runner.run(

@@ -33,7 +33,7 @@ import threading
 
 import numpy as np
 
-from shennong_b200 import engine
+from shennong_b200 import _lib, engine
 from shennong_b200.audio import Audio
 
 _ALIGN = 8
@@ -371,15 +371,31 @@ class StreamRunner:
     later cudaFree, a device-wide synchronisation -- on every call).
     """
 
+    # Streams and slot buffers are shared by every runner of the process (the
+    # batch entry points build a runner per call): keyed by what they hold,
+    # they only grow.  `_pool_lock` serialises the runs that use them.
+    _pool = {}
+    _pool_lock = threading.Lock()
+
     def __init__(self, pipe, chunk_utts=None, chunk_samples=None,
                  block_bytes=None, nslots=3):
         self.pipe = pipe
         # defaults: 512 utterances or 96 M samples (192 MB of PCM) per chunk,
         # 8 GiB of base + final features per block of speakers
         env = os.environ.get
-        self.chunk_utts = int(chunk_utts or env('SNB_STREAM_CHUNK_UTTS', 512))
+        default_utts, default_samples = 512, 96_000_000
+        if pipe.pitch is not None:
+            # the pitch tracker follows one utterance per warp, sequentially
+            # over its frames: a chunk must fill a whole round of it (4 736
+            # utterances on a B200) or the kernel runs mostly empty
+            wave = int(_lib.lib().snb_pitch_wave_utts(
+                engine.pitch_plan(pipe.pitch[0]._pitch_opts()).handle))
+            default_utts = max(default_utts, wave)
+            default_samples = max(default_samples, wave * 170_000)
+        self.chunk_utts = int(
+            chunk_utts or env('SNB_STREAM_CHUNK_UTTS', default_utts))
         self.chunk_samples = int(
-            chunk_samples or env('SNB_STREAM_CHUNK_SAMPLES', 96_000_000))
+            chunk_samples or env('SNB_STREAM_CHUNK_SAMPLES', default_samples))
         self.block_bytes = int(
             block_bytes or env('SNB_STREAM_BLOCK_BYTES', 8 << 30))
         self.nslots = int(nslots)
@@ -393,11 +409,15 @@ class StreamRunner:
     # -- buffers ---------------------------------------------------------------
     def _buffers(self, span, rows, block_rows, staging):
         torch = engine.require_cuda()
-        pipe, st = self.pipe, self._state
+        pipe = self.pipe
+        key = (torch.cuda.current_device(), self.nslots, pipe.out_dim,
+               pipe.base_dim)
+        st = StreamRunner._pool.get(key)
         if st is None:
-            st = self._state = {
+            st = StreamRunner._pool[key] = {
                 'streams': tuple(torch.cuda.Stream() for _ in range(4)),
                 'span': 0, 'rows': 0, 'block_rows': 0, 'staging': 0}
+        self._state = st
         if st['span'] < span:
             st['span'] = span
             st['pcm'] = [torch.empty(span, dtype=torch.int16, device='cuda')
@@ -454,7 +474,7 @@ class StreamRunner:
             self.utt_group = groups
         if plan is None:
             plan = self.plan(source.lengths, groups)
-        with self._lock:
+        with StreamRunner._pool_lock:
             return self._run(torch, source, plan, groups, warps, out_host,
                              gather, seed)
 

@@ -383,8 +383,9 @@ def test_unaligned_utterance_offsets():
 
 
 def test_dither_statistics():
-    """dither = N(0, 1) per sample, independent across samples and frames
-    (Kaldi draws every sample anew): on a silent signal the frame energy is a
+    """dither = N(0, 1) per sample of every extracted window, drawn anew for
+    each frame (Kaldi dithers the frame's private copy, overlapping frames do
+    not share their noise): on a silent signal the frame energy is a
     chi-square with 400 degrees of freedom -- mean 400, variance 800 -- and
     the energies of different frames are uncorrelated, on the fused fast path
     (counter-based Box-Muller) as on the generic one"""
@@ -401,10 +402,7 @@ def test_dither_statistics():
         assert abs(e.var() / (2 * dof) - 1.0) < 0.1
         for lag in (1, 2, 3, 7):
             c = np.corrcoef(e[:-lag], e[lag:])[0, 1]
-            # frames overlap (shift 160 of 400/640 samples): the expected
-            # correlation of the energies is the shared fraction
-            shared = max(0.0, 1.0 - lag * 160 / dof)
-            assert abs(c - shared) < 0.05, (lag, c, shared)
+            assert abs(c) < 0.05, (lag, c)
         # another seed gives other noise
         e2 = proc.process(silence).data.reshape(-1)
         assert abs(np.corrcoef(e, e2)[0, 1]) < 0.05

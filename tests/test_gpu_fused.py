@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import scale_close, synth_utterance
+from conftest import cmvn_close, scale_close, synth_utterance
 from shennong_b200 import Audio, engine
 from shennong_b200.fused import FusedPipeline
 from shennong_b200.postprocessor import DeltaPostProcessor, VadPostProcessor
@@ -43,7 +43,8 @@ def test_device_pipeline_matches_oracle(signals):
     for i, sig in enumerate(signals):
         if offs[i + 1] - offs[i] < 3:
             continue    # variance of 1-2 frames is floored: x * 1e10 noise
-        scale_close(out[offs[i]:offs[i + 1]], oracle_pipeline(sig), tol=2e-4)
+        cmvn_close(out[offs[i]:offs[i + 1]], oracle_pipeline(sig),
+                   oracle.features('mfcc', sig))
     st = engine.to_host(stats)
     assert st.shape == (len(signals), 2, 14)
     assert np.array_equal(st[:, 0, -1], np.diff(offs).astype(np.float64))
@@ -74,10 +75,12 @@ def test_speaker_cmvn_and_vad(signals):
         for i, (sig, s) in enumerate(zip(signals, speakers)):
             if s != spk or offs[i + 1] - offs[i] < 3:
                 continue
-            ref = oracle.deltas(
-                oracle.cmvn_apply(oracle.features('mfcc', sig), ref_stats),
-                1, 2)
-            scale_close(out[offs[i]:offs[i + 1]], ref, tol=2e-4)
+            base = oracle.features('mfcc', sig)
+            ref = oracle.deltas(oracle.cmvn_apply(base, ref_stats), 1, 2)
+            count = ref_stats[0, -1]
+            sigma = np.sqrt(ref_stats[1, :-1] / count
+                            - (ref_stats[0, :-1] / count) ** 2)
+            cmvn_close(out[offs[i]:offs[i + 1]], ref, base, sigma=sigma)
 
 
 def test_pitch_columns(signals):
@@ -92,7 +95,8 @@ def test_pitch_columns(signals):
     assert out.shape[1] == 42
     for i, sig in enumerate(sigs):
         block = out[offs[i]:offs[i + 1]]
-        scale_close(block[:, :39], oracle_pipeline(sig), tol=2e-4)
+        cmvn_close(block[:, :39], oracle_pipeline(sig),
+                   oracle.features('mfcc', sig))
         raw = pitch[0].process(Audio(sig, 16000))
         ref = pitch[1].process(raw).data
         assert np.allclose(block[:, 39:], ref, atol=1e-5)
