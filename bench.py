@@ -91,7 +91,11 @@ def parse_args():
                     help='collection inside the step for N > 1: libsnb kernel '
                     'storing into the peers\' buffers over NVLink (p2p), '
                     'NCCL all-gather (nccl)')
-    ap.add_argument('--gather-ctas', type=int, default=64)
+    ap.add_argument('--gather-ctas', type=int, default=0,
+                    help='CTAs (128 threads) of the peer-store kernel; 0: 74 '
+                    'per peer, at most 296 (few CTAs disturb the overlapped '
+                    'compute least, many fill the links when the collection '
+                    'is the longer of the two)')
     ap.add_argument('--force-chunks', action='store_true',
                     help='cut the step in --gather-chunks chunks even without '
                     'collection (diagnosis of the chunking cost)')
@@ -503,7 +507,8 @@ def main():
     base = (None if pipe.simple else torch.empty(
         (total_frames, pipe.base_dim), dtype=torch.float32, device='cuda'))
     gathered, s_comm, peers = None, None, None
-    if world > 1 and args.gather != 'none':
+    if (world > 1 and args.gather != 'none') or (
+            args.force_chunks and args.gather == 'p2p'):
         s_comm = torch.cuda.Stream()
         sizes = [world * c['rows'] * pipe.out_dim for c in chunks]
         bases = np.concatenate(([0], np.cumsum(sizes)))
@@ -518,11 +523,13 @@ def main():
         gathered = [flat[int(bases[k]):int(bases[k + 1])].view(
             world * c['rows'], pipe.out_dim) for k, c in enumerate(chunks)]
 
+    gather_ctas = args.gather_ctas or min(296, 74 * max(world - 1, 1))
+
     def collect(k, c, r0, r1):
         """rows of chunk k -> every rank (queued on the current stream)"""
         if peers is not None:
             peers.push(out[r0:r1], int(bases[k]) + rank * c['rows']
-                       * pipe.out_dim, ctas=args.gather_ctas)
+                       * pipe.out_dim, ctas=gather_ctas)
         else:
             dist.all_gather_into_tensor(gathered[k], out[r0:r1])
 
@@ -601,13 +608,15 @@ def main():
         barrier()
         gt = torch.tensor([g0.elapsed_time(g1) / 3], device='cuda',
                           dtype=torch.float64)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        if world > 1:
+            dist.all_reduce(gt, op=dist.ReduceOp.MAX)
         nbytes = int(out.numel() * 4)
         gather = {'in_step': True, 'chunks': len(chunks),
                   'alone_ms': float(gt[0]), 'bytes_per_rank': nbytes,
                   'recv_gbs_per_rank':
                   (world - 1) * nbytes / (float(gt[0]) * 1e-3) / 1e9,
                   'how': args.gather,
+                  'ctas': gather_ctas if peers is not None else None,
                   'api': ('distributed.PeerGather: one libsnb kernel per '
                           'chunk stores its rows into the result buffers of '
                           'all ranks (CUDA IPC peer memory over NVLink), a '
@@ -624,12 +633,14 @@ def main():
         # and every other rank's rows: float64 checksums of the blocks
         sums = torch.zeros(world, dtype=torch.float64, device='cuda')
         sums[rank] = out.double().sum()
-        dist.all_reduce(sums)
+        if world > 1:
+            dist.all_reduce(sums)
         got = torch.stack([torch.cat([
             g.view(world, -1, pipe.out_dim)[r] for g in gathered]).double().sum()
             for r in range(world)])
         okay = torch.tensor([float(torch.equal(got, sums))], device='cuda')
-        dist.all_reduce(okay, op=dist.ReduceOp.MIN)
+        if world > 1:
+            dist.all_reduce(okay, op=dist.ReduceOp.MIN)
         gather['rows_of_all_ranks_match_checksums'] = bool(okay.item() == 1.0)
 
     # ---- parity check on rows of every rank (dither 0, outside the clock) ---

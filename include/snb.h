@@ -337,7 +337,8 @@ int snb_peer_buffer_close(void *d_ptr);
 int snb_peer_buffer_destroy(void *d_ptr);
 /* copies nfloats (multiple of 4) contiguous floats at d_src to
  * dst[p] + dst_offset_floats for p < ndst (HOST array of DEVICE pointers, own
- * buffer and mapped peer buffers alike; ndst <= 16), by `ctas` CTAs (<= 0: 32)
+ * buffer and mapped peer buffers alike; ndst <= 16), by `ctas` CTAs of 128
+ * threads (<= 0: 296)
  * on `stream`.  The rows are visible to a peer once this launch has completed
  * and the ranks have synchronised. */
 int snb_gather_rows(const float *d_src, int64_t nfloats, float *const *dst,

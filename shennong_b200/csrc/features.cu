@@ -811,9 +811,16 @@ generic_features_kernel(const GenArgs a) {
     __syncwarp();
     // load (reflect at edges), dither
     float lsum = 0.0f;
-    for (int i0 = 2 * lane; i0 < W; i0 += 64) {          // a lane takes sample PAIRS: one Box-Muller for two
+    // dither: the generator of the fused path (one MUFU-only Box-Muller per
+    // sample pair, keyed by the frame)
+    const uint32_t nkey = frame_noise_key(a.seed, static_cast<uint64_t>(row));
+    const float nc = -1.3862943611198906f * p.fo.dither * p.fo.dither;     // -2 ln 2 dither^2
+    for (int i0 = 2 * lane; i0 < W; i0 += 64) {          // a lane takes sample PAIRS
       float g[2] = {0.0f, 0.0f};
-      if (p.fo.dither != 0.0f) gauss_pair(a.seed, static_cast<uint64_t>(row), i0 >> 1, &g[0], &g[1]);
+      if (p.fo.dither != 0.0f) {
+        const float2 nz = dither_pair(nkey, static_cast<uint32_t>(i0 >> 1), nc);
+        g[0] = nz.x; g[1] = nz.y;
+      }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int i = i0 + e;
@@ -821,7 +828,7 @@ generic_features_kernel(const GenArgs a) {
         int64_t k = start + i;
         while (k < 0 || k >= n) k = (k < 0) ? (-k - 1) : (2 * n - 1 - k);
         float v = a.pcm_f32 ? a.pcm_f32[utt_off + k] : static_cast<float>(a.pcm[utt_off + k]);
-        if (p.fo.dither != 0.0f) v = fmaf(p.fo.dither, g[e], v);
+        v += g[e];
         buf_a[i] = v;
         lsum += v;
       }

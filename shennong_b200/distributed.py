@@ -190,7 +190,7 @@ class PeerGather:
         if self.size > 1:
             dist.barrier(group=group)
 
-    def push(self, src, offset_floats, ctas=32):
+    def push(self, src, offset_floats, ctas=296):
         """`src` (contiguous float32 device tensor, a multiple of 4 elements)
         -> floats [offset, offset + src.numel()) of every rank's buffer"""
         import ctypes

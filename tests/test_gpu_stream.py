@@ -109,7 +109,10 @@ def wav_corpus(tmp_path_factory):
 
 def test_process_all_streams_wav_files(wav_corpus, monkeypatch):
     monkeypatch.setenv('SNB_STREAM_CHUNK_UTTS', '4')
-    utts = Utterances([(e[0], e[1]) + tuple(e[3:]) for e in wav_corpus])
+    # (one format for all: whole files as the segment [0, duration])
+    utts = Utterances([
+        (e[0], e[1]) + (tuple(e[3:]) or (0.0, Audio.scan(e[1]).duration))
+        for e in wav_corpus])
     proc = MfccProcessor(dither=0)
     feats = proc.process_all(utts, njobs=3)
     assert set(feats.keys()) == {e[0] for e in wav_corpus}
@@ -140,7 +143,10 @@ def test_extract_features_streamed_small_chunks(wav_corpus, monkeypatch):
         'mfcc', with_pitch='kaldi', with_cmvn=True, with_delta=True)
     config['mfcc']['dither'] = 0
     config['pitch']['postprocessing']['delta_pitch_noise_stddev'] = 0
-    utts = Utterances(wav_corpus)
+    # (one format for all: whole files as the segment [0, duration])
+    utts = Utterances([
+        tuple(e[:3]) + (tuple(e[3:]) or (0.0, Audio.scan(e[1]).duration))
+        for e in wav_corpus])
     ref = pipeline.extract_features(config, utts)
     monkeypatch.setenv('SNB_STREAM_CHUNK_UTTS', '3')
     monkeypatch.setenv('SNB_STREAM_BLOCK_BYTES', str(4 * (13 + 42) * 1200))
