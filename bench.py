@@ -87,15 +87,26 @@ def parse_args():
                     'pitch tracker when the pipeline has pitch)')
     ap.add_argument('--gather-chunks', type=int, default=8,
                     help='chunks of the device-resident step for N > 1')
-    ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl', 'none'],
-                    help='collection inside the step for N > 1: libsnb kernel '
-                    'storing into the peers\' buffers over NVLink (p2p), '
-                    'NCCL all-gather (nccl)')
+    ap.add_argument('--gather', default='ce',
+                    choices=['ce', 'bulk', 'stores', 'nccl', 'none'],
+                    help='collection inside the step for N > 1: pushes into '
+                    'the peers\' result buffers over NVLink (CUDA IPC) by the '
+                    'copy engines (ce), by one-warp CTAs driving the TMA unit '
+                    '(bulk), by plain 16-byte stores (stores); or NCCL '
+                    'all-gather (nccl)')
     ap.add_argument('--gather-ctas', type=int, default=0,
-                    help='CTAs (128 threads) of the peer-store kernel; 0: 74 '
-                    'per peer, at most 296 (few CTAs disturb the overlapped '
-                    'compute least, many fill the links when the collection '
-                    'is the longer of the two)')
+                    help='CTAs of the bulk / stores kernels (0: 148 / 74 per '
+                    'peer, at most 296)')
+    ap.add_argument('--gather-base-chunks', type=int, default=-1,
+                    help='chunks that travel as base rows + normalisation '
+                    'table, the receivers redoing normalise + delta (peer '
+                    'modes, pipelines with deltas); -1: half of the chunks '
+                    'with 7 or more peers, else none')
+    ap.add_argument('--gather-fanout', type=int, default=1,
+                    help='link-load experiment: every push is delivered this '
+                    'many times to each peer (N = 2 with 7 carries the NVLink '
+                    'traffic per GPU of N = 8); `value` then counts the frames '
+                    'of the real ranks only')
     ap.add_argument('--force-chunks', action='store_true',
                     help='cut the step in --gather-chunks chunks even without '
                     'collection (diagnosis of the chunking cost)')
@@ -469,7 +480,7 @@ def main():
 
     # ---- corpus: device-generated, the first utterances host-generated -----
     # (those are the ones the CPU arms and the parity check read)
-    nhost = min(nutts, 2048 if (rank == 0 and not args.no_cpu) else 8)
+    nhost = min(nutts, 2048 if (world == 1 and not args.no_cpu) else 8)
     host_head = synth_host(rank * nutts, nhost)
     pcm_dev = torch.cat([synth_pcm_device(nutts, rank, torch),
                          torch.zeros(64, dtype=torch.int16, device='cuda')])
@@ -502,41 +513,75 @@ def main():
         chunks.append(dict(packed=packed, batches=batches, rows=rows,
                            row0=total_frames, spk=speakers[b:e]))
         total_frames += rows
-    out = torch.empty((total_frames, pipe.out_dim), dtype=torch.float32,
-                      device='cuda')
     base = (None if pipe.simple else torch.empty(
         (total_frames, pipe.base_dim), dtype=torch.float32, device='cuda'))
-    gathered, s_comm, peers = None, None, None
+    gathered, s_comm, coll = None, None, None
+    peer_modes = ('ce', 'bulk', 'stores')
+    gather_ctas = args.gather_ctas
+    if args.gather == 'stores' and not gather_ctas:
+        gather_ctas = min(296, 74 * max(world - 1, 1))
+    base_chunks = 0
     if (world > 1 and args.gather != 'none') or (
-            args.force_chunks and args.gather == 'p2p'):
-        s_comm = torch.cuda.Stream()
-        sizes = [world * c['rows'] * pipe.out_dim for c in chunks]
-        bases = np.concatenate(([0], np.cumsum(sizes)))
-        if args.gather == 'p2p':
-            from shennong_b200.distributed import PeerGather
-            peers = PeerGather(int(bases[-1]))
-            flat = peers.tensor
+            args.force_chunks and args.gather in peer_modes):
+        if args.gather in peer_modes:
+            from shennong_b200.distributed import ChunkCollector
+            hybrid_ok = (pipe.delta is not None and pipe.pitch is None
+                         and pipe.cmvn != 'speaker')
+            base_chunks = args.gather_base_chunks
+            if base_chunks < 0:
+                # with 8 ranks the all-gather of the final rows outlasts the
+                # extraction: half of the chunks travel as base rows
+                links = (world - 1) * args.gather_fanout
+                base_chunks = len(chunks) // 2 if links >= 6 else 0
+            if not hybrid_ok:
+                base_chunks = 0
+            coll = ChunkCollector(
+                pipe, [c['batches']['feat'].frame_offsets for c in chunks],
+                how=args.gather, base_chunks=base_chunks, ctas=gather_ctas,
+                fanout=args.gather_fanout)
+            # the rows are produced IN the gather buffer (own block of every
+            # chunk): the collection writes the peers only
+            outs = [coll.out_view(k) for k in range(len(chunks))]
+            gathered = [coll.result(k) for k in range(len(chunks))]
+            out = None
         else:
+            s_comm = torch.cuda.Stream()
+            sizes = [world * c['rows'] * pipe.out_dim for c in chunks]
+            bases = np.concatenate(([0], np.cumsum(sizes)))
             flat = torch.empty(int(bases[-1]), dtype=torch.float32,
                                device='cuda')
-        # chunk k of the result: [world, rows_k, D], rank-major
-        gathered = [flat[int(bases[k]):int(bases[k + 1])].view(
-            world * c['rows'], pipe.out_dim) for k, c in enumerate(chunks)]
+            # chunk k of the result: [world, rows_k, D], rank-major
+            gathered = [list(flat[int(bases[k]):int(bases[k + 1])].view(
+                world, c['rows'], pipe.out_dim))
+                for k, c in enumerate(chunks)]
+            flat_chunks = [flat[int(bases[k]):int(bases[k + 1])].view(
+                world * c['rows'], pipe.out_dim)
+                for k, c in enumerate(chunks)]
+    if coll is None:
+        out = torch.empty((total_frames, pipe.out_dim), dtype=torch.float32,
+                          device='cuda')
+        outs = [out[c['row0']:c['row0'] + c['rows']] for c in chunks]
 
-    gather_ctas = args.gather_ctas or min(296, 74 * max(world - 1, 1))
-
-    def collect(k, c, r0, r1):
-        """rows of chunk k -> every rank (queued on the current stream)"""
-        if peers is not None:
-            peers.push(out[r0:r1], int(bases[k]) + rank * c['rows']
-                       * pipe.out_dim, ctas=gather_ctas)
+    def collect(k):
+        """rows of chunk k -> every rank (queued behind the chunk's work)"""
+        if coll is not None:
+            coll.collect(k)
         else:
-            dist.all_gather_into_tensor(gathered[k], out[r0:r1])
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            with torch.cuda.stream(s_comm):
+                s_comm.wait_event(done)
+                dist.all_gather_into_tensor(flat_chunks[k], outs[k])
+
+    def finish():
+        if coll is not None:
+            coll.finish()
+        else:
+            torch.cuda.current_stream().wait_stream(s_comm)
 
     ev_feat = []
 
     def step(timed, seed):
-        cur = torch.cuda.current_stream()
         for k, c in enumerate(chunks):
             r0, r1 = c['row0'], c['row0'] + c['rows']
             if timed:
@@ -544,23 +589,19 @@ def main():
                         torch.cuda.Event(enable_timing=True))
                 ev_feat.append(pair)
                 engine.feature_events = pair
+            bbuf = coll.base_view(k) if coll is not None else None
+            if bbuf is None and base is not None:
+                bbuf = base[r0:r1]
             pipe.run_device(
                 c['packed'], speakers=c['spk'] if pipe.cmvn == 'speaker'
-                else None, seed=seed, out=out[r0:r1], plans=plans,
-                base_buf=None if base is None else base[r0:r1],
-                batches=c['batches'])
+                else None, seed=seed, out=outs[k], plans=plans,
+                base_buf=bbuf, batches=c['batches'],
+                norm_out=coll.norm_view(k) if coll is not None else None)
             engine.feature_events = None
             if gathered is not None:
-                done = torch.cuda.Event()
-                done.record(cur)
-                with torch.cuda.stream(s_comm):
-                    s_comm.wait_event(done)
-                    collect(k, c, r0, r1)
+                collect(k)
         if gathered is not None:
-            if peers is not None:
-                with torch.cuda.stream(s_comm):
-                    peers.arrive()
-            cur.wait_stream(s_comm)      # the step ends with the collection
+            finish()                     # the step ends with the collection
 
     for w in range(args.warmup):
         step(False, 100 + w)
@@ -600,44 +641,62 @@ def main():
         barrier()
         g0.record()
         for _ in range(3):
-            for k, c in enumerate(chunks):
-                collect(k, c, c['row0'], c['row0'] + c['rows'])
-            if peers is not None:
-                peers.arrive()
+            for k in range(len(chunks)):
+                collect(k)
+            finish()
         g1.record()
         barrier()
         gt = torch.tensor([g0.elapsed_time(g1) / 3], device='cuda',
                           dtype=torch.float64)
         if world > 1:
             dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        if out is None:
+            out = torch.cat(outs)
         nbytes = int(out.numel() * 4)
+        # bytes a rank sends to EACH peer per step
+        as_base = set(coll.base_ids) if coll is not None else set()
+        link = sum(c['rows'] * 4 * (pipe.base_dim if k in as_base
+                                    else pipe.out_dim)
+                   for k, c in enumerate(chunks))
         gather = {'in_step': True, 'chunks': len(chunks),
                   'alone_ms': float(gt[0]), 'bytes_per_rank': nbytes,
+                  'link_bytes_per_peer': int(link),
                   'recv_gbs_per_rank':
-                  (world - 1) * nbytes / (float(gt[0]) * 1e-3) / 1e9,
-                  'how': args.gather,
-                  'ctas': gather_ctas if peers is not None else None,
-                  'api': ('distributed.PeerGather: one libsnb kernel per '
-                          'chunk stores its rows into the result buffers of '
-                          'all ranks (CUDA IPC peer memory over NVLink), a '
-                          '4-byte all-reduce closes the step'
-                          if peers is not None else
+                  (world - 1) * args.gather_fanout * link
+                  / (float(gt[0]) * 1e-3) / 1e9,
+                  'how': args.gather, 'fanout': args.gather_fanout,
+                  'ctas': gather_ctas if coll is not None else None,
+                  'chunks_as_base_rows': base_chunks,
+                  'api': ('distributed.ChunkCollector: the rows of a chunk are '
+                          'produced in the rank\'s own result buffer and '
+                          'pushed into the result buffers of the other ranks '
+                          '(CUDA IPC peer memory over NVLink) by '
+                          + {'ce': 'the copy engines (snb_gather_rows_ce)',
+                             'bulk': 'one-warp CTAs driving the TMA unit '
+                             '(snb_gather_rows_bulk)',
+                             'stores': 'a kernel of 16-byte stores '
+                             '(snb_gather_rows)'}.get(args.gather, '') +
+                          ', a 4-byte all-reduce closes the step'
+                          + ('; %d chunks travel as base rows + '
+                             'normalisation table (a third of the bytes) and '
+                             'every receiver redoes the normalise + delta '
+                             'launch on them (bit-identical rows)'
+                             % base_chunks if base_chunks else '')
+                          if coll is not None else
                           'all_gather_into_tensor of every chunk (NCCL over '
                           'NVLink)') + '; on a second stream, chunk k travels '
                          'while chunk k + 1 is computed; `alone_ms` is the '
                          'same collection without compute'}
         # the gathered result of the last step against the local rows
-        mine = torch.cat([g.view(world, -1, pipe.out_dim)[rank]
-                          for g in gathered])
+        mine = torch.cat([g[rank] for g in gathered])
         gather['own_rows_intact'] = bool(torch.equal(mine, out))
         # and every other rank's rows: float64 checksums of the blocks
         sums = torch.zeros(world, dtype=torch.float64, device='cuda')
         sums[rank] = out.double().sum()
         if world > 1:
             dist.all_reduce(sums)
-        got = torch.stack([torch.cat([
-            g.view(world, -1, pipe.out_dim)[r] for g in gathered]).double().sum()
-            for r in range(world)])
+        got = torch.stack([torch.cat([g[r] for g in gathered]).double().sum()
+                           for r in range(world)])
         okay = torch.tensor([float(torch.equal(got, sums))], device='cuda')
         if world > 1:
             dist.all_reduce(okay, op=dist.ReduceOp.MIN)
@@ -689,7 +748,8 @@ def main():
         / (ms_per_step * 1e-3) / 1e9,
     }
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:       # (rank 0 at N = 1 only: at N > 1
+        # the rank is bound to its share of the host cores)
         cpu, _, _ = cpu_baseline(args.config, host_head, nhost, args.dither)
 
     result = {

@@ -345,6 +345,38 @@ int snb_gather_rows(const float *d_src, int64_t nfloats, float *const *dst,
                     int32_t ndst, int64_t dst_offset_floats, int32_t ctas,
                     void *stream);
 
+/* The same collection without the load/store pipes of the SMs.
+ * snb_gather_rows_bulk: one-warp CTAs (<= 0: 148) whose lane 0 drives the TMA
+ * unit: 8 KB pieces global -> shared -> every destination
+ * (cp.async.bulk both ways), 24 KB of shared memory per CTA; meant to run on
+ * a second stream UNDER the feature kernel of the next chunk.
+ * snb_gather_rows_ce: one cudaMemcpyAsync per destination on internal
+ * per-destination streams (copy engines), forked from and joined to `stream`.
+ * A destination equal to the source (rows produced in place in the own
+ * buffer) is skipped by both. */
+int snb_gather_rows_bulk(const float *d_src, int64_t nfloats, float *const *dst,
+                         int32_t ndst, int64_t dst_offset_floats, int32_t ctas,
+                         void *stream);
+int snb_gather_rows_ce(const float *d_src, int64_t nfloats, float *const *dst,
+                       int32_t ndst, int64_t dst_offset_floats, void *stream);
+
+/* ---- input step on the host ------------------------------------
+ * The reference decodes every utterance with scipy.io.wavfile in its joblib
+ * workers (audio.py:243-286) and slices [tstart, tstop] from the decoded array
+ * (audio.py:520-561, utterances.py:171-176).  The payload of a RIFF/WAVE file
+ * with PCM encoding, one channel and 16 bits IS the int16 signal of this path:
+ * these two calls find it and read it into caller-owned (pinned) memory on
+ * `nthreads` native threads.
+ * snb_wav_scan_batch: data_offset[i] (bytes, -1 when file i is anything else
+ * than mono 16-bit PCM or cannot be read), nsamples[i], rate[i]. */
+int snb_wav_scan_batch(const char *const *paths, int64_t n, int64_t *data_offset,
+                       int64_t *nsamples, int32_t *rate, int32_t nthreads);
+/* reads nbytes[i] bytes at byte offsets[i] of file paths[i] into dst[i];
+ * SNB_ERR_VALUE (and *first_failed = smallest failing index) on a short read */
+int snb_read_segments(const char *const *paths, const int64_t *offsets,
+                      const int64_t *nbytes, void *const *dst, int64_t n,
+                      int32_t nthreads, int64_t *first_failed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,10 @@ SIGNATURES = {
     'snb_peer_buffer_close': (ctypes.c_int, [vp]),
     'snb_peer_buffer_destroy': (ctypes.c_int, [vp]),
     'snb_gather_rows': (ctypes.c_int, [vp, i64, vp, i32, i64, i32, vp]),
+    'snb_gather_rows_bulk': (ctypes.c_int, [vp, i64, vp, i32, i64, i32, vp]),
+    'snb_gather_rows_ce': (ctypes.c_int, [vp, i64, vp, i32, i64, vp]),
+    'snb_wav_scan_batch': (ctypes.c_int, [vp, i64, vp, vp, vp, i32]),
+    'snb_read_segments': (ctypes.c_int, [vp, vp, vp, vp, i64, i32, vp]),
 }
 
 _lib = None

@@ -105,7 +105,6 @@ class Audio:
             raise ValueError(f'cannot scan audio file {filename}') from None
 
     @classmethod
-    @functools.lru_cache(maxsize=None)
     def wav_layout(cls, filename):
         """(data offset in bytes, nsamples, sample rate) of a mono 16-bit PCM
         WAV file, None for anything else (compressed, float, multi-channel, malformed):

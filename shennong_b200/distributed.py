@@ -149,14 +149,19 @@ class PeerGather:
     Every rank owns a float32 result buffer of `nfloats`; the buffers are
     mapped in every process of the node through CUDA IPC
     (``snb_peer_buffer_*``) and :meth:`push` writes a block of finished rows
-    at the same offset of ALL of them with one libsnb kernel
-    (``snb_gather_rows``) on the current stream -- the all-gather of the
-    north star as posted writes, issued by the producer as soon as a chunk is
-    done, with no rendezvous per chunk.  :meth:`arrive` is the one
+    at the same offset of ALL of them (``snb_gather_rows_ce`` /
+    ``snb_gather_rows_bulk`` / ``snb_gather_rows``) on the current stream --
+    the all-gather of the north star as posted writes, issued by the producer
+    as soon as a chunk is done, with no rendezvous per chunk.  The pipeline
+    can write its rows straight into the own buffer (:attr:`tensor`): the
+    gather staging buffer IS the result.  :meth:`arrive` is the one
     synchronisation of a step: a 4-byte all-reduce queued behind the pushes.
     """
 
-    def __init__(self, nfloats, group=None):
+    def __init__(self, nfloats, group=None, fanout=1):
+        """`fanout` > 1 (link-load experiments only): every peer buffer is
+        `fanout` times as large and receives `fanout` copies of each push, so
+        that two GPUs carry the NVLink traffic of ``1 + fanout`` ranks"""
         import ctypes
         import torch
         from shennong_b200 import _lib
@@ -164,12 +169,13 @@ class PeerGather:
         self.rank, self.size = world()
         self.group = group
         self.nfloats = int(nfloats)
+        self.fanout = max(1, int(fanout))
         L = _lib.lib()
         self._lib = L
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
         _lib.check(L.snb_peer_buffer_create(
-            self.nfloats * 4, ctypes.byref(ptr), handle))
+            self.nfloats * 4 * self.fanout, ctypes.byref(ptr), handle))
         self._own = ptr.value
         handles = all_gather_objects(bytes(handle), group)
         self._opened = []
@@ -182,26 +188,48 @@ class PeerGather:
             buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
             _lib.check(L.snb_peer_buffer_open(buf, ctypes.byref(peer)))
             self._opened.append(peer.value)
-            ptrs.append(peer.value)
-        self._ptrs = (ctypes.c_void_p * self.size)(*ptrs)
+            ptrs += [peer.value + 4 * self.nfloats * j
+                     for j in range(self.fanout)]
+        self._nptrs = len(ptrs)
+        self._ptrs = (ctypes.c_void_p * self._nptrs)(*ptrs)
         self.tensor = torch.as_tensor(
             _DeviceBuffer(self._own, self.nfloats), device='cuda')
         self._flag = torch.zeros(1, dtype=torch.int32, device='cuda')
         if self.size > 1:
             dist.barrier(group=group)
 
-    def push(self, src, offset_floats, ctas=296):
+    def push(self, src, offset_floats, ctas=0, how='ce'):
         """`src` (contiguous float32 device tensor, a multiple of 4 elements)
-        -> floats [offset, offset + src.numel()) of every rank's buffer"""
+        -> floats [offset, offset + src.numel()) of every rank's buffer
+
+        `how`: 'ce' copy engines (one peer copy per rank on internal
+        streams, joined to the current stream: no SM is used), 'bulk' one-warp
+        CTAs driving the TMA unit (``snb_gather_rows_bulk``), 'stores' plain
+        16-byte stores by `ctas` CTAs of 128 threads.  `src` may be the
+        destination slice of the own buffer (rows produced in place): that
+        copy is skipped.
+        """
         import ctypes
         import torch
         from shennong_b200 import _lib
         if not src.is_contiguous():
             raise ValueError('contiguous rows expected')
-        _lib.check(self._lib.snb_gather_rows(
-            ctypes.c_void_p(src.data_ptr()), src.numel(), self._ptrs,
-            self.size, int(offset_floats), int(ctas),
-            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        src_p = ctypes.c_void_p(src.data_ptr())
+        if how == 'ce':
+            _lib.check(self._lib.snb_gather_rows_ce(
+                src_p, src.numel(), self._ptrs, self._nptrs,
+                int(offset_floats), stream))
+        elif how == 'bulk':
+            _lib.check(self._lib.snb_gather_rows_bulk(
+                src_p, src.numel(), self._ptrs, self._nptrs,
+                int(offset_floats), int(ctas), stream))
+        elif how == 'stores':
+            _lib.check(self._lib.snb_gather_rows(
+                src_p, src.numel(), self._ptrs, self._nptrs,
+                int(offset_floats), int(ctas) or 296, stream))
+        else:
+            raise ValueError(f'unknown collection method {how}')
 
     def arrive(self):
         """queued on the current stream: completes when every rank's pushes
@@ -222,6 +250,183 @@ class PeerGather:
         if self._own:
             self._lib.snb_peer_buffer_destroy(ctypes.c_void_p(self._own))
             self._own = None
+
+
+def _ceil4(n):
+    return (int(n) + 3) // 4 * 4
+
+
+class ChunkCollector:
+    """Collection of a chunked, device-resident extraction inside the step
+
+    Every rank runs the same :class:`FusedPipeline` over its own shard, cut in
+    chunks of the same geometry on every rank (`chunk_offsets[k]` are the
+    frame offsets of chunk k: equal shards, e.g. a corpus of equal-length
+    utterances; ragged shards go through the chunk-wise NCCL gather of
+    :mod:`shennong_b200.stream`).  The rows of chunk k are PRODUCED in this
+    rank's block of the result buffer (:meth:`out_view`) and pushed to the
+    same block of every peer's buffer while chunk k + 1 is computed
+    (:class:`PeerGather`, own stream); :meth:`finish` closes the step: every
+    rank then holds ``result(k)`` = [world, rows_k, D] for every chunk.
+
+    `base_chunks` > 0 (pipelines with deltas, CMVN per utterance or none):
+    for that many chunks only the BASE rows [rows_k, d] and the normalisation
+    table of the chunk travel -- a third of the bytes for MFCC + delta +
+    delta-delta -- and every receiver redoes the normalise + delta launch on
+    them (``snb_cmvn_apply_deltas``, the same kernel on the same inputs: the
+    rows are bit-identical to the sender's).  It trades NVLink time for
+    HBM-bound recomputation: with 8 GPUs the all-gather of 39 columns (10.9 GB
+    received per rank and step in BASELINE configs[2]) takes longer than the
+    extraction itself.  The base-row chunks are the ones just before the last
+    chunk: the links carry full rows from the first chunk on, the receivers'
+    launches run at the end of the step under the push of the last chunk.
+    """
+
+    def __init__(self, pipe, chunk_offsets, how='ce', base_chunks=0, ctas=0,
+                 fanout=1, group=None):
+        import torch
+        from shennong_b200 import engine
+        self.pipe = pipe
+        self.rank, self.size = world()
+        self.how, self.ctas = how, int(ctas)
+        self.offsets = [np.ascontiguousarray(o, dtype=np.int64)
+                        for o in chunk_offsets]
+        self.rows = [int(o[-1]) for o in self.offsets]
+        self.nchunks = n = len(self.rows)
+        D, d = pipe.out_dim, pipe.base_dim
+        order = pipe.delta.order if pipe.delta is not None else 0
+        nb = int(base_chunks)
+        if nb and (order == 0 or pipe.cmvn == 'speaker'
+                   or pipe.pitch is not None):
+            raise ValueError(
+                'base-rows collection needs a pipeline with deltas, without '
+                'pitch columns and without CMVN by speaker')
+        nb = min(nb, n) if self.size > 1 else 0
+        first = max(n - 1 - nb, 0)
+        self.base_ids = list(range(first, first + nb))
+        # result buffer: chunk k = `size` blocks of stride[k] floats
+        self.stride = [_ceil4(r * D) for r in self.rows]
+        self.at = np.concatenate(
+            ([0], np.cumsum([self.size * st for st in self.stride])))
+        self.peers = PeerGather(int(self.at[-1]), group, fanout)
+        self.staging = None
+        self.bstride, self.nstride, self.bat = {}, {}, {}
+        self.layouts, self.nutts = {}, {}
+        if nb:
+            at = 0
+            for k in self.base_ids:
+                self.nutts[k] = len(self.offsets[k]) - 1
+                self.bstride[k] = _ceil4(self.rows[k] * d)
+                self.nstride[k] = (_ceil4(self.nutts[k] * 2 * d)
+                                   if pipe.cmvn else 0)
+                self.bat[k] = at
+                at += self.size * (self.bstride[k] + self.nstride[k])
+                self.layouts[k] = engine.RowLayout(
+                    frame_offsets=self.offsets[k])
+            self.staging = PeerGather(at, group, fanout)
+        self.comm = torch.cuda.Stream()
+        self._base_arrived = None
+
+    # -- views ---------------------------------------------------------------
+    def _block(self, k, r):
+        a = int(self.at[k]) + r * self.stride[k]
+        return self.peers.tensor[a:a + self.rows[k] * self.pipe.out_dim].view(
+            self.rows[k], self.pipe.out_dim)
+
+    def out_view(self, k):
+        """[rows_k, D]: where this rank's pipeline writes chunk k"""
+        return self._block(k, self.rank)
+
+    def result(self, k):
+        """[world, rows_k, D] views of chunk k (valid after :meth:`finish`)"""
+        return [self._block(k, r) for r in range(self.size)]
+
+    def _base_block(self, k, r):
+        a = self.bat[k] + r * self.bstride[k]
+        d = self.pipe.base_dim
+        return self.staging.tensor[a:a + self.rows[k] * d].view(
+            self.rows[k], d)
+
+    def _norm_block(self, k, r):
+        if not self.nstride[k]:
+            return None
+        d = self.pipe.base_dim
+        a = self.bat[k] + self.size * self.bstride[k] + r * self.nstride[k]
+        return self.staging.tensor[a:a + self.nutts[k] * 2 * d].view(
+            self.nutts[k], 2, d)
+
+    def base_view(self, k):
+        """[rows_k, d] buffer for the base rows of chunk k (``base_buf`` of
+        ``run_device``) when the chunk travels as base rows, else None"""
+        return self._base_block(k, self.rank) if k in self.bat else None
+
+    def norm_view(self, k):
+        """``norm_out`` of ``run_device`` for chunk k (or None)"""
+        return self._norm_block(k, self.rank) if k in self.bat else None
+
+    # -- the step --------------------------------------------------------------
+    def collect(self, k):
+        """Queues the push of chunk k behind the work queued so far on the
+        current stream (call right after ``run_device`` of the chunk)"""
+        import torch
+        if self.size == 1 and self.peers.fanout == 1:
+            return
+        cur = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(done)
+            if k in self.bat:
+                a = self.bat[k] + self.rank * self.bstride[k]
+                src = self.staging.tensor[a:a + self.bstride[k]]
+                self.staging.push(src, a, ctas=self.ctas, how=self.how)
+                if self.nstride[k]:
+                    a = (self.bat[k] + self.size * self.bstride[k]
+                         + self.rank * self.nstride[k])
+                    src = self.staging.tensor[a:a + self.nstride[k]]
+                    self.staging.push(src, a, ctas=self.ctas, how=self.how)
+                if k == self.base_ids[-1]:
+                    self.staging.arrive()
+                    self._base_arrived = torch.cuda.Event()
+                    self._base_arrived.record(self.comm)
+            else:
+                a = int(self.at[k]) + self.rank * self.stride[k]
+                src = self.peers.tensor[a:a + self.stride[k]]
+                self.peers.push(src, a, ctas=self.ctas, how=self.how)
+
+    def finish(self):
+        """Queues the end of the step on the current stream: the receivers'
+        normalise + delta launches on the base rows of the other ranks, then
+        the arrival of every rank's pushes"""
+        import torch
+        from shennong_b200 import engine
+        cur = torch.cuda.current_stream()
+        if self.size == 1:
+            cur.wait_stream(self.comm)
+            return
+        if self.base_ids:
+            cur.wait_event(self._base_arrived)
+            pipe = self.pipe
+            order, window = pipe.delta.order, pipe.delta.window
+            for k in self.base_ids:
+                for r in range(self.size):
+                    if r == self.rank:
+                        continue
+                    engine.deltas(
+                        self._base_block(k, r), self.layouts[k], order,
+                        window, norm=self._norm_block(k, r),
+                        out=self._block(k, r)[:, :pipe.feat_dim])
+            # (a peer may overwrite the staging only after these launches:
+            # the closing all-reduce waits for them)
+            self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            self.peers.arrive()
+        cur.wait_stream(self.comm)
+
+    def close(self):
+        self.peers.close()
+        if self.staging is not None:
+            self.staging.close()
 
 
 def allreduce_stats(stats, group=None):

@@ -319,11 +319,12 @@ def cmvn_reduce_groups(utt_stats, group_ptr, group_utts, ngroups):
     return out
 
 
-def cmvn_norm(stats, norm_vars=True, reverse=False):
+def cmvn_norm(stats, norm_vars=True, reverse=False, out=None):
     """float32 [ngroups, 2, dim] (offset, scale) table from float64 stats"""
     torch = require_cuda()
     ngroups, dim = stats.shape[0], stats.shape[2] - 1
-    norm = torch.empty((ngroups, 2, dim), dtype=torch.float32, device='cuda')
+    norm = out if out is not None else torch.empty(
+        (ngroups, 2, dim), dtype=torch.float32, device='cuda')
     _lib.check(_lib.lib().snb_cmvn_norm_from_stats(
         _ptr(stats), ngroups, dim, int(bool(norm_vars)), int(bool(reverse)),
         _ptr(norm), _stream_ptr()))

@@ -145,7 +145,7 @@ class FusedPipeline:
 
     # -- pass two --------------------------------------------------------------
     def pass_two(self, base, out, frame_offsets, ustats, group=None,
-                 ngroups=0, layout=None):
+                 ngroups=0, layout=None, norm_out=None):
         """Normalisation table from the statistics and the normalise + delta
         launch over `base` rows described by `frame_offsets` (host int64
         [U+1]) or `layout`.  `group` (host int array) pools the
@@ -164,7 +164,8 @@ class FusedPipeline:
                 stats = engine.cmvn_reduce_groups(ustats, ptr, order, ngroups)
                 utt_group = torch.from_numpy(
                     group.astype(np.int32)).to('cuda', non_blocking=True)
-            norm = engine.cmvn_norm(stats, self.norm_vars, False)
+            norm = engine.cmvn_norm(stats, self.norm_vars, False,
+                                    out=norm_out)
         order = self.delta.order if self.delta is not None else 0
         window = self.delta.window if self.delta is not None else 1
         engine.deltas(base, layout, order, window, norm=norm,
@@ -174,7 +175,7 @@ class FusedPipeline:
 
     def run_device(self, packed, speakers=None, warps=None, seed=None,
                    out=None, plans=None, base_buf=None, batch=None,
-                   batches=None, stats_out=None):
+                   batches=None, stats_out=None, norm_out=None):
         """Runs the whole pipeline on a PackedAudio already on the device
 
         Returns (out [total_frames, out_dim] device tensor, frame_offsets
@@ -185,7 +186,10 @@ class FusedPipeline:
         intermediate base features (chunked pipelines reuse it); `batches`
         the descriptors of :meth:`make_batches` already created for `packed`;
         `stats_out` an optional [U, 2, base_dim + 1] float64 device tensor
-        for the per-utterance statistics.  When features and pitch disagree
+        for the per-utterance statistics, `norm_out` one [U or groups, 2,
+        base_dim] float32 for the normalisation table (both are what a peer
+        needs to redo pass two on the base rows:
+        :class:`shennong_b200.distributed.ChunkCollector`).  When features and pitch disagree
         by one or two frames on some utterance, ``self.valid_rows`` holds the
         rows to keep per utterance (None otherwise).
         """
@@ -226,7 +230,7 @@ class FusedPipeline:
                 self._group_names = names
             stats = self.pass_two(
                 base, out, None, ustats, group, ngroups,
-                layout=engine.RowLayout(batch=batch))
+                layout=engine.RowLayout(batch=batch), norm_out=norm_out)
             group = self._last[2]
         self._last = (batch, base, keep, self._last)   # keep buffers alive
         return out, batch.frame_offsets, stats, group

@@ -82,8 +82,6 @@ class AudioSource:
         padded = (self.lengths + _ALIGN - 1) // _ALIGN * _ALIGN
         self.pstarts = np.concatenate(([0], np.cumsum(padded)))
         self.workers = max(1, int(workers))
-        self._pool = (concurrent.futures.ThreadPoolExecutor(self.workers)
-                      if self.workers > 1 else None)
 
     def span(self, b, e):
         return int(self.pstarts[e] - self.pstarts[b]) + 64
@@ -108,22 +106,43 @@ class AudioSource:
         """Packs utterances [b, e) into `staging` (pinned int16 tensor);
         returns (tensor slice, relative starts)"""
         rel = self.pstarts[b:e] - self.pstarts[b]
-        view = staging.numpy()
-        idx = range(b, e)
-        if self._pool is not None and e - b > 8:
-            step = (e - b + self.workers - 1) // self.workers
-
-            def work(lo):
-                for i in range(lo, min(lo + step, e)):
+        files = [i for i in range(b, e) if isinstance(self.items[i], tuple)]
+        if files:
+            # WAV payloads: one native call, `workers` threads preading into
+            # the staging buffer (snb_read_segments, no GIL)
+            self._read_files(files, rel, b, staging.data_ptr())
+        if len(files) < e - b:
+            view = staging.numpy()
+            for i in range(b, e):
+                if not isinstance(self.items[i], tuple):
                     s = int(rel[i - b])
                     self._load(i, view[s:s + int(self.lengths[i])])
-            list(self._pool.map(work, range(b, e, step)))
-        else:
-            for i in idx:
-                s = int(rel[i - b])
-                self._load(i, view[s:s + int(self.lengths[i])])
         n = int(rel[-1] + self.lengths[e - 1])
         return staging[:n], rel
+
+    def _read_files(self, files, rel, b, base_ptr):
+        import ctypes
+        n = len(files)
+        paths = (ctypes.c_char_p * n)()
+        offsets = np.empty(n, dtype=np.int64)
+        nbytes = np.empty(n, dtype=np.int64)
+        dst = np.empty(n, dtype=np.uint64)
+        for j, i in enumerate(files):
+            path, offset, first, _ = self.items[i]
+            paths[j] = os.fsencode(path)
+            offsets[j] = offset + 2 * first
+            nbytes[j] = 2 * int(self.lengths[i])
+            dst[j] = base_ptr + 2 * int(rel[i - b])
+        failed = ctypes.c_int64(-1)
+        code = _lib.lib().snb_read_segments(
+            paths, offsets.ctypes.data_as(ctypes.c_void_p),
+            nbytes.ctypes.data_as(ctypes.c_void_p),
+            dst.ctypes.data_as(ctypes.c_void_p), n, self.workers,
+            ctypes.byref(failed))
+        if code != 0:
+            bad = self.items[files[failed.value]][0] if failed.value >= 0 \
+                else '?'
+            raise ValueError(f'{bad}: cannot read file, truncated data')
 
 
 def _to_int16(data):
@@ -645,6 +664,32 @@ class StreamRunner:
 # --------------------------------------------------------------------------
 # corpus level: what the batch entry points of the host API call
 # --------------------------------------------------------------------------
+def wav_layouts(paths, nthreads=None):
+    """[(data offset in bytes, nsamples, sample rate) or None] for `paths`:
+    the header walk of every DISTINCT file on native threads
+    (``snb_wav_scan_batch``); None for anything that is not a mono 16-bit PCM
+    WAV file.  Nothing is cached: a file that changed between two calls is
+    seen as it is now."""
+    import ctypes
+    distinct = list(dict.fromkeys(str(p) for p in paths))
+    n = len(distinct)
+    if n == 0:
+        return []
+    arr = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in distinct])
+    offset = np.empty(n, dtype=np.int64)
+    nsamples = np.empty(n, dtype=np.int64)
+    rate = np.empty(n, dtype=np.int32)
+    threads = nthreads or min(len(os.sched_getaffinity(0)), 32)
+    _lib.check(_lib.lib().snb_wav_scan_batch(
+        arr, n, offset.ctypes.data_as(ctypes.c_void_p),
+        nsamples.ctypes.data_as(ctypes.c_void_p),
+        rate.ctypes.data_as(ctypes.c_void_p), threads))
+    found = {p: ((int(offset[i]), int(nsamples[i]), int(rate[i]))
+                 if offset[i] >= 0 else None)
+             for i, p in enumerate(distinct)}
+    return [found[str(p)] for p in paths]
+
+
 def audio_items(utts, sample_rate=None):
     """What :class:`AudioSource` reads for the utterances `utts`:
     (items, sample counts, all int16).  Segments of mono 16-bit PCM WAV files
@@ -654,8 +699,8 @@ def audio_items(utts, sample_rate=None):
     `sample_rate` the reference's process-time check of the signal's rate is
     applied (processor/base.py:415-419)."""
     items, lengths, int16 = [], [], True
-    for utt in utts:
-        layout = Audio.wav_layout(utt.audio_file)
+    layouts = wav_layouts([utt.audio_file for utt in utts])
+    for utt, layout in zip(utts, layouts):
         if layout is None:
             meta = Audio.scan(utt.audio_file)
             nchannels, rate = meta.nchannels, meta.sample_rate

@@ -53,21 +53,65 @@ WORKER = textwrap.dedent('''
     rows, dim = 1000 + 8 * rank, 12
     total = sum(1000 + 8 * r for r in range(size)) * dim
     peers = PeerGather(total)
-    block = (rank + 1) * 1000.0 + torch.arange(
-        rows * dim, dtype=torch.float32, device='cuda').view(rows, dim) / 7
     offset = sum(1000 + 8 * r for r in range(rank)) * dim
-    peers.push(block, offset, ctas=8)
-    peers.arrive()
-    torch.cuda.synchronize()
-    got = peers.tensor.clone()
-    at = 0
-    for r in range(size):
-        n = (1000 + 8 * r) * dim
-        want = (r + 1) * 1000.0 + torch.arange(
-            n, dtype=torch.float32, device='cuda') / 7
-        assert torch.equal(got[at:at + n], want), (rank, r)
-        at += n
+    for round_, how in enumerate(('ce', 'bulk', 'stores', 'ce')):
+        base = (rank + 1) * 1000.0 + 10000.0 * round_
+        block = base + torch.arange(
+            rows * dim, dtype=torch.float32, device='cuda').view(rows, dim) / 7
+        if round_ == 3:
+            # rows produced in place in the own buffer: only the peers are written
+            mine = peers.tensor[offset:offset + rows * dim].view(rows, dim)
+            mine.copy_(block)
+            block = mine
+        peers.push(block, offset, ctas=8, how=how)
+        peers.arrive()
+        torch.cuda.synchronize()
+        got = peers.tensor.clone()
+        at = 0
+        for r in range(size):
+            n = (1000 + 8 * r) * dim
+            want = (r + 1) * 1000.0 + 10000.0 * round_ + torch.arange(
+                n, dtype=torch.float32, device='cuda') / 7
+            assert torch.equal(got[at:at + n], want), (rank, r, how)
+            at += n
+        dist.barrier()
     peers.close()
+    # ---- chunked device-resident step with the collection inside --------------
+    from shennong_b200.distributed import ChunkCollector
+    n_utt, n_samp, n_chunk = 12, 32000, 3
+    mine = [synth_utterance(100 + rank * n_utt + i, n_samp) for i in range(n_utt)]
+    pipe = FusedPipeline(MfccProcessor(dither=0), delta=DeltaPostProcessor(),
+                         cmvn='utterance')
+    plans = pipe._plans()
+    per = n_utt // n_chunk
+    packs = [engine.PackedAudio(mine[k * per:(k + 1) * per]) for k in range(n_chunk)]
+    batches = [pipe.make_batches(plans, p) for p in packs]
+    want_local, _, _, _ = pipe.run_device(engine.PackedAudio(mine))
+    want = [torch.empty_like(want_local) for _ in range(size)]
+    dist.all_gather(want, want_local.contiguous())
+    for how, nb in (('ce', 0), ('ce', 2), ('bulk', 3), ('stores', 1)):
+        coll = ChunkCollector(
+            pipe, [b['feat'].frame_offsets for b in batches], how=how,
+            base_chunks=nb, ctas=8)
+        for rep in range(2):         # twice: buffers are reused across steps
+            for k in range(n_chunk):
+                pipe.run_device(packs[k], out=coll.out_view(k), plans=plans,
+                                base_buf=coll.base_view(k), batches=batches[k],
+                                norm_out=coll.norm_view(k))
+                coll.collect(k)
+            coll.finish()
+            torch.cuda.synchronize()
+            for r in range(size):
+                got = torch.cat([coll.result(k)[r] for k in range(n_chunk)])
+                assert torch.equal(got, want[r]), (how, nb, rep, rank, r)
+            if rep == 0:             # poison: the second step must rewrite all
+                dist.barrier()
+                for k in range(n_chunk):
+                    for r in range(size):
+                        coll.result(k)[r].fill_(float('nan'))
+                torch.cuda.synchronize()
+                dist.barrier()
+        coll.close()
     # ---- the host API, sharded: every rank gets the whole collection ---------
     root = os.environ['SNB_WAVS']
     if rank == 0:

@@ -99,6 +99,29 @@ def test_wav_layout_and_audio_source(tmp_path):
         assert n == len(sig) and rate == 16000
         items.append((path, offset, 0, n))
         lengths.append(n)
+    # the native header walk (snb_wav_scan_batch) against the Python one,
+    # incl. files it must refuse, a missing file and an extra chunk before
+    # `data`
+    listed = str(tmp_path / 'listed.wav')
+    raw = open(paths[1], 'rb').read()
+    at = raw.index(b'data')
+    extra = b'LIST' + (6).to_bytes(4, 'little') + b'abcdef'
+    body = raw[:at] + extra + raw[at:]
+    body = body[:4] + (len(body) - 8).to_bytes(4, 'little') + body[8:]
+    open(listed, 'wb').write(body)
+    probe = paths + [fpath, stereo, str(tmp_path / 'missing.wav'), listed,
+                     paths[0]]
+    assert stream.wav_layouts(probe, nthreads=3) == [
+        Audio.wav_layout(p) for p in probe]
+    assert stream.wav_layouts(probe)[-2][1] == len(sigs[1])
+    # a truncated file is reported like the reference's loader does
+    short = str(tmp_path / 'short.wav')
+    open(short, 'wb').write(open(paths[0], 'rb').read()[:-100])
+    off, n, _ = stream.wav_layouts([short])[0]
+    with pytest.raises(ValueError, match='cannot read file'):
+        src = stream.AudioSource([(short, off, 0, n + 50)], [n + 50])
+        import torch
+        src.window(0, 1, torch.zeros(src.span(0, 1), dtype=torch.int16))
     # a segment of a file, an in-memory int16 array and a float Audio
     offset = Audio.wav_layout(paths[0])[0]
     items += [(paths[0], offset, 1000, 5000), sigs[2],
