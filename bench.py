@@ -80,7 +80,7 @@ def parse_args():
     ap.add_argument('--dither', type=float, default=1.0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-api', action='store_true')
-    ap.add_argument('--api-utts', type=int, default=2000)
+    ap.add_argument('--api-utts', type=int, default=4000)
     ap.add_argument('--chunk-utts', type=int, default=0,
                     help='utterances per chunk of the host pipeline (e2e); '
                     '0: the runner\'s default (512, or one round of the '
@@ -100,8 +100,10 @@ def parse_args():
     ap.add_argument('--gather-base-chunks', type=int, default=-1,
                     help='chunks that travel as base rows + normalisation '
                     'table, the receivers redoing normalise + delta (peer '
-                    'modes, pipelines with deltas); -1: half of the chunks '
-                    'with 7 or more peers, else none')
+                    'modes, pipelines with deltas); -1: 5 of 8 chunks with 6 '
+                    'or more peers (measured optimum under the NVLink load '
+                    'of 8 ranks, profiles/r02_n2_collection_variants_c.txt), '
+                    'else none')
     ap.add_argument('--gather-fanout', type=int, default=1,
                     help='link-load experiment: every push is delivered this '
                     'many times to each peer (N = 2 with 7 carries the NVLink '
@@ -530,9 +532,9 @@ def main():
             base_chunks = args.gather_base_chunks
             if base_chunks < 0:
                 # with 8 ranks the all-gather of the final rows outlasts the
-                # extraction: half of the chunks travel as base rows
+                # extraction: 5 of 8 chunks travel as base rows
                 links = (world - 1) * args.gather_fanout
-                base_chunks = len(chunks) // 2 if links >= 6 else 0
+                base_chunks = (5 * len(chunks) + 4) // 8 if links >= 6 else 0
             if not hybrid_ok:
                 base_chunks = 0
             coll = ChunkCollector(
@@ -915,7 +917,7 @@ def end_to_end(args, pipe, pcm_dev, out, starts, lengths, speakers,
     del scratch
     spk = speakers if pipe.cmvn == 'speaker' else None
     nrep = max(2, min(args.steps, 5))
-    for _ in range(2):                                           # warm-up
+    for _ in range(3):                                           # warm-up
         pipe.run_host(host_pcm, starts, lengths, out_host=out_host,
                       chunk_utts=args.chunk_utts or None, speakers=spk)
     barrier()

@@ -142,6 +142,9 @@ def lib():
         L.orc_cmvn_apply.restype = i32
         L.orc_cmvn_apply.argtypes = [P, i32, i32, i32, P, i64]
         L.orc_sliding_window_cmn.argtypes = [P, i64, i32, i32, i32, i32, i32, P]
+        L.orc_resample_num_out.restype = i64
+        L.orc_resample_num_out.argtypes = [i64, i32, i32]
+        L.orc_resample.argtypes = [P, i64, i32, i32, f32, i32, P]
         L.orc_vad_energy.argtypes = [P, i64, i32, f32, f32, i32, f32, P]
         L.orc_pitch_num_frames.restype = i64
         L.orc_pitch_num_frames.argtypes = [i64, P]
@@ -396,6 +399,17 @@ def pitch(signal, **kw):
     got = L.orc_compute_kaldi_pitch(_ptr(wave), len(wave), ctypes.byref(po),
                                     _ptr(out))
     assert got == nf, (got, nf)
+    return out
+
+
+def resample(signal, rate_in, rate_out, cutoff=0.0, num_zeros=0):
+    """Kaldi's flushed LinearResample of a whole signal (float32 result)"""
+    wave = np.ascontiguousarray(signal, dtype=np.float32)
+    L = lib()
+    n = L.orc_resample_num_out(len(wave), int(rate_in), int(rate_out))
+    out = np.zeros(n, dtype=np.float32)
+    L.orc_resample(_ptr(wave), len(wave), int(rate_in), int(rate_out),
+                   float(cutoff), int(num_zeros), _ptr(out))
     return out
 
 

@@ -999,6 +999,22 @@ static void linear_resample(const float *in, int64_t n_in, int32_t rate_in,
   free(weights); free(first_index); free(nw);
 }
 
+/* Whole-signal resampling with Kaldi's LinearResample, flushed (what
+ * kaldi::ResampleWaveform does: resample.cc; cutoff <= 0 selects its default
+ * 0.99 * 0.5 * min(rate_in, rate_out), num_zeros <= 0 its default 6).  The
+ * step before the path (reference: shennong/audio.py:358-423 calls
+ * sox or scipy for the same purpose). */
+int64_t orc_resample_num_out(int64_t n_in, int32_t rate_in, int32_t rate_out) {
+  return linear_resample_num_out(n_in, rate_in, rate_out, 1.0f, 1, 1);
+}
+void orc_resample(const float *in, int64_t n_in, int32_t rate_in, int32_t rate_out,
+                  float cutoff, int32_t num_zeros, float *out /*[orc_resample_num_out]*/) {
+  if (cutoff <= 0.0f) cutoff = 0.99f * 0.5f * (float)(rate_in < rate_out ? rate_in : rate_out);
+  if (num_zeros <= 0) num_zeros = 6;
+  linear_resample(in, n_in, rate_in, rate_out, cutoff, num_zeros, out,
+                  orc_resample_num_out(n_in, rate_in, rate_out));
+}
+
 static int32_t nccf_window_size(const orc_pitch_opts *o) {
   return (int32_t)((double)o->resample_freq * (double)o->frame_length_ms / 1000.0);
 }

@@ -144,6 +144,11 @@ void orc_vad_energy(const float *feats, int64_t nframes, int32_t dim,
                     float *out /*[nframes] 0/1*/);
 
 /* pitch */
+/* Kaldi LinearResample of a whole signal, flushed (kaldi::ResampleWaveform);
+ * cutoff <= 0 / num_zeros <= 0 select Kaldi's defaults */
+int64_t orc_resample_num_out(int64_t n_in, int32_t rate_in, int32_t rate_out);
+void orc_resample(const float *in, int64_t n_in, int32_t rate_in, int32_t rate_out,
+                  float cutoff, int32_t num_zeros, float *out);
 int64_t orc_pitch_num_frames(int64_t nsamples, const orc_pitch_opts *o);
 int32_t orc_pitch_num_lags(const orc_pitch_opts *o);
 int64_t orc_compute_kaldi_pitch(const float *wave, int64_t nsamples,

@@ -83,6 +83,56 @@ def main():
         feats = procs[kind](dither=0).process(Audio(sig, 16000))
         row(f'{kind} (oracle)', feats, oracle.features(kind, sig))
     print(f'# worst max|a-b|/max|ref| = {worst:.2e} (gate 1e-4)')
+    pitch_rows(oracle, pcm, synth_utterance)
+
+
+def pitch_rows(oracle, pcm, synth_utterance):
+    """Kaldi pitch: index work (the Viterbi state of every frame) must be
+    bit-exact against the oracle; known answers the oracle cannot fake"""
+    from conftest import numpy_process_pitch
+    from shennong_b200 import Audio, Features
+    from shennong_b200.processor import (
+        KaldiPitchPostProcessor, KaldiPitchProcessor)
+    print('## Kaldi pitch against the CPU oracle: frames, frames on the same '
+          'Viterbi state, NCCF column bit-equal, max|NCCF diff|')
+    cases = [('test.wav defaults', pcm, {}),
+             ('test.wav min_f0=60 max_f0=350', pcm, {'min_f0': 60, 'max_f0': 350}),
+             ('test.wav shift 20 ms length 50 ms', pcm,
+              {'frame_shift': 0.02, 'frame_length': 0.05}),
+             ('test.wav penalty_factor 0.3', pcm, {'penalty_factor': 0.3}),
+             ('test.wav delta_pitch 0.002 (1040 states)', pcm, {'delta_pitch': 0.002}),
+             ('test.wav upsample_filter_width 7', pcm, {'upsample_filter_width': 7})]
+    cases += [(f'synthetic 10 s utterance {u}', synth_utterance(u, 160000), {})
+              for u in (3, 11, 42)]
+    all_same = True
+    for name, sig, kw in cases:
+        out = KaldiPitchProcessor(**kw).process(Audio(sig, 16000)).data
+        ref = oracle.pitch(sig, **kw)
+        same = int((out[:, 1] == ref[:, 1]).sum())
+        all_same = all_same and same == len(ref) and np.array_equal(out[:, 0], ref[:, 0])
+        print(f'{name:44s} {len(ref):5d} {same:5d}  '
+              f'{bool(np.array_equal(out[:, 0], ref[:, 0]))}  '
+              f'{np.abs(out[:, 0] - ref[:, 0]).max():.1e}')
+    print(f'# state sequence and NCCF bit-exact on every case: {all_same}')
+    print('## known answers: 5-harmonic tone of fundamental f0 (3 s), median '
+          '|f0_est / f0 - 1| over the frames (lag grid step 0.5 %)')
+    t = np.arange(48000) / 16000.0
+    for f0 in (60, 85, 120, 170, 240, 350):
+        x = sum(3000.0 / h * np.sin(2 * np.pi * h * f0 * t + 0.3 * h) for h in range(1, 6))
+        sig = np.round(x).astype(np.int16)
+        out = KaldiPitchProcessor(min_f0=50, max_f0=400).process(Audio(sig, 16000)).data
+        rel = np.abs(out[:, 1] / f0 - 1.0)
+        print(f'f0 = {f0:3d} Hz   median {np.median(rel):.2e}   p90 {np.percentile(rel, 90):.2e}'
+              f'   median NCCF {np.median(out[:, 0]):.3f}')
+    print('## post-processing against a float64 numpy evaluation of the published '
+          'formulas (pitch_crepe.py:246-253 for POV): max abs error per column '
+          '(pov feature, normalised log-pitch, delta, raw log-pitch)')
+    raw = KaldiPitchProcessor().process(Audio(pcm, 16000))
+    post = KaldiPitchPostProcessor(delta_pitch_noise_stddev=0, add_raw_log_pitch=True).process(raw)
+    want = numpy_process_pitch(raw.data)
+    print('test.wav  ' + '  '.join(f'{e:.1e}' for e in np.abs(post.data - want).max(axis=0)))
+    ref = oracle.process_pitch(raw.data, delta_pitch_noise_stddev=0, add_raw_log_pitch=True)
+    print('against the oracle: ' + '  '.join(f'{e:.1e}' for e in np.abs(post.data - ref).max(axis=0)))
 
 
 if __name__ == '__main__':
