@@ -87,13 +87,14 @@ def parse_args():
                     'pitch tracker when the pipeline has pitch)')
     ap.add_argument('--gather-chunks', type=int, default=8,
                     help='chunks of the device-resident step for N > 1')
-    ap.add_argument('--gather', default='ce',
-                    choices=['ce', 'bulk', 'stores', 'nccl', 'none'],
+    ap.add_argument('--gather', default='auto',
+                    choices=['auto', 'ce', 'bulk', 'stores', 'nccl', 'none'],
                     help='collection inside the step for N > 1: pushes into '
                     'the peers\' result buffers over NVLink (CUDA IPC) by the '
                     'copy engines (ce), by one-warp CTAs driving the TMA unit '
                     '(bulk), by plain 16-byte stores (stores); or NCCL '
-                    'all-gather (nccl)')
+                    'all-gather (nccl); auto: the fastest of ce / bulk / '
+                    'nccl in a few untimed trial steps before the warm-up')
     ap.add_argument('--gather-ctas', type=int, default=0,
                     help='CTAs of the bulk / stores kernels (0: 148 / 74 per '
                     'peer, at most 296)')
@@ -517,73 +518,54 @@ def main():
         total_frames += rows
     base = (None if pipe.simple else torch.empty(
         (total_frames, pipe.base_dim), dtype=torch.float32, device='cuda'))
-    gathered, s_comm, coll = None, None, None
-    peer_modes = ('ce', 'bulk', 'stores')
-    gather_ctas = args.gather_ctas
-    if args.gather == 'stores' and not gather_ctas:
-        gather_ctas = min(296, 74 * max(world - 1, 1))
-    base_chunks = 0
-    if (world > 1 and args.gather != 'none') or (
-            args.force_chunks and args.gather in peer_modes):
-        if args.gather in peer_modes:
-            from shennong_b200.distributed import ChunkCollector
-            hybrid_ok = (pipe.delta is not None and pipe.pitch is None
-                         and pipe.cmvn != 'speaker')
-            base_chunks = args.gather_base_chunks
-            if base_chunks < 0:
-                # with 8 ranks the all-gather of the final rows outlasts the
-                # extraction: 5 of 8 chunks travel as base rows
-                links = (world - 1) * args.gather_fanout
-                base_chunks = (5 * len(chunks) + 4) // 8 if links >= 6 else 0
-            if not hybrid_ok:
-                base_chunks = 0
-            coll = ChunkCollector(
-                pipe, [c['batches']['feat'].frame_offsets for c in chunks],
-                how=args.gather, base_chunks=base_chunks, ctas=gather_ctas,
-                fanout=args.gather_fanout)
-            # the rows are produced IN the gather buffer (own block of every
-            # chunk): the collection writes the peers only
-            outs = [coll.out_view(k) for k in range(len(chunks))]
-            gathered = [coll.result(k) for k in range(len(chunks))]
-            out = None
-        else:
-            s_comm = torch.cuda.Stream()
-            sizes = [world * c['rows'] * pipe.out_dim for c in chunks]
-            bases = np.concatenate(([0], np.cumsum(sizes)))
-            flat = torch.empty(int(bases[-1]), dtype=torch.float32,
-                               device='cuda')
-            # chunk k of the result: [world, rows_k, D], rank-major
-            gathered = [list(flat[int(bases[k]):int(bases[k + 1])].view(
-                world, c['rows'], pipe.out_dim))
-                for k, c in enumerate(chunks)]
-            flat_chunks = [flat[int(bases[k]):int(bases[k + 1])].view(
-                world * c['rows'], pipe.out_dim)
-                for k, c in enumerate(chunks)]
-    if coll is None:
+    modes = ('ce', 'bulk', 'stores', 'nccl')
+    collecting = (world > 1 and args.gather != 'none') or (
+        args.force_chunks and args.gather in modes)
+    hybrid_ok = (pipe.delta is not None and pipe.pitch is None
+                 and pipe.cmvn != 'speaker')
+    links = (world - 1) * args.gather_fanout
+    C = {'coll': None, 'how': None, 'base_chunks': 0, 'ctas': 0}
+
+    def default_base_chunks():
+        # with 8 ranks the all-gather of the final rows outlasts the
+        # extraction: 5 of 8 chunks travel as base rows
+        if not hybrid_ok:
+            return 0
+        if args.gather_base_chunks >= 0:
+            return args.gather_base_chunks
+        return (5 * len(chunks) + 4) // 8 if links >= 6 else 0
+
+    def set_collection(how, nb):
+        from shennong_b200.distributed import ChunkCollector
+        if C['coll'] is not None:
+            C['coll'].close()
+            C['coll'] = None
+            torch.cuda.empty_cache()
+        ctas = args.gather_ctas
+        if how == 'stores' and not ctas:
+            ctas = min(296, 74 * max(world - 1, 1))
+        C.update(how=how, base_chunks=nb, ctas=ctas)
+        C['coll'] = ChunkCollector(
+            pipe, [c['batches']['feat'].frame_offsets for c in chunks],
+            how=how, base_chunks=nb, ctas=ctas,
+            fanout=args.gather_fanout if how != 'nccl' else 1)
+        # the rows are produced IN the gather buffer (own block of every
+        # chunk): the collection writes the peers only
+        C['outs'] = [C['coll'].out_view(k) for k in range(len(chunks))]
+
+    out = None
+    if collecting:
+        set_collection('ce' if args.gather == 'auto' else args.gather,
+                       default_base_chunks())
+    else:
         out = torch.empty((total_frames, pipe.out_dim), dtype=torch.float32,
                           device='cuda')
-        outs = [out[c['row0']:c['row0'] + c['rows']] for c in chunks]
-
-    def collect(k):
-        """rows of chunk k -> every rank (queued behind the chunk's work)"""
-        if coll is not None:
-            coll.collect(k)
-        else:
-            done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream())
-            with torch.cuda.stream(s_comm):
-                s_comm.wait_event(done)
-                dist.all_gather_into_tensor(flat_chunks[k], outs[k])
-
-    def finish():
-        if coll is not None:
-            coll.finish()
-        else:
-            torch.cuda.current_stream().wait_stream(s_comm)
+        C['outs'] = [out[c['row0']:c['row0'] + c['rows']] for c in chunks]
 
     ev_feat = []
 
     def step(timed, seed):
+        coll, outs = C['coll'], C['outs']
         for k, c in enumerate(chunks):
             r0, r1 = c['row0'], c['row0'] + c['rows']
             if timed:
@@ -600,10 +582,48 @@ def main():
                 base_buf=bbuf, batches=c['batches'],
                 norm_out=coll.norm_view(k) if coll is not None else None)
             engine.feature_events = None
-            if gathered is not None:
-                collect(k)
-        if gathered is not None:
-            finish()                     # the step ends with the collection
+            if coll is not None:
+                coll.collect(k)
+        if coll is not None:
+            coll.finish()                # the step ends with the collection
+
+    def trial_ms(nsteps=3):
+        """max over ranks of the mean step time (one untimed step first)"""
+        step(False, 7)
+        barrier()
+        t0, t1 = (torch.cuda.Event(enable_timing=True),
+                  torch.cuda.Event(enable_timing=True))
+        t0.record()
+        for i in range(nsteps):
+            step(False, 8 + i)
+        t1.record()
+        barrier()
+        t = torch.tensor([t0.elapsed_time(t1) / nsteps], device='cuda',
+                         dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- --gather auto: the collection method is chosen by measurement ------
+    # (before the warm-up; every rank sees the same max-over-ranks times)
+    calibration = None
+    if collecting and args.gather == 'auto':
+        calibration = {}
+        nb0 = default_base_chunks()
+        for how in ('ce', 'bulk', 'nccl'):
+            if how != C['how'] or nb0 != C['base_chunks']:
+                set_collection(how, nb0)
+            calibration['%s/%d' % (how, nb0)] = trial_ms()
+        best = min(calibration, key=calibration.get).split('/')[0]
+        if hybrid_ok and args.gather_base_chunks < 0 and links >= 3:
+            # and the number of base-row chunks around the default
+            for nb in sorted({max(nb0 - 1, 0), min(nb0 + 1, len(chunks) - 1),
+                              min(nb0 + 2, len(chunks) - 1)} - {nb0}):
+                set_collection(best, nb)
+                calibration['%s/%d' % (best, nb)] = trial_ms()
+        how, nb = min(calibration, key=calibration.get).split('/')
+        if (how, int(nb)) != (C['how'], C['base_chunks']):
+            set_collection(how, int(nb))
 
     for w in range(args.warmup):
         step(False, 100 + w)
@@ -637,58 +657,63 @@ def main():
 
     # ---- collection alone (N > 1): what the overlap hides --------------------
     gather = None
-    if gathered is not None:
+    if C['coll'] is not None:
+        coll = C['coll']
+        nck = len(chunks)
         g0, g1 = (torch.cuda.Event(enable_timing=True),
                   torch.cuda.Event(enable_timing=True))
         barrier()
         g0.record()
         for _ in range(3):
-            for k in range(len(chunks)):
-                collect(k)
-            finish()
+            for k in range(nck):
+                coll.collect(k)
+            coll.finish()
         g1.record()
         barrier()
         gt = torch.tensor([g0.elapsed_time(g1) / 3], device='cuda',
                           dtype=torch.float64)
         if world > 1:
             dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        if out is None:
-            out = torch.cat(outs)
+        out = torch.cat(C['outs'])
+        gathered = [coll.result(k) for k in range(nck)]
         nbytes = int(out.numel() * 4)
         # bytes a rank sends to EACH peer per step
-        as_base = set(coll.base_ids) if coll is not None else set()
+        as_base = set(coll.base_ids)
         link = sum(c['rows'] * 4 * (pipe.base_dim if k in as_base
                                     else pipe.out_dim)
                    for k, c in enumerate(chunks))
-        gather = {'in_step': True, 'chunks': len(chunks),
+        fan = args.gather_fanout if C['how'] != 'nccl' else 1
+        what = {'ce': 'pushed into the result buffers of the other ranks '
+                '(CUDA IPC peer memory over NVLink) by the copy engines '
+                '(snb_gather_rows_ce)',
+                'bulk': 'pushed into the result buffers of the other ranks '
+                '(CUDA IPC peer memory over NVLink) by one-warp CTAs driving '
+                'the TMA unit (snb_gather_rows_bulk)',
+                'stores': 'pushed into the result buffers of the other ranks '
+                '(CUDA IPC peer memory over NVLink) by a kernel of 16-byte '
+                'stores (snb_gather_rows)',
+                'nccl': 'all-gathered chunk by chunk (NCCL over NVLink)'}
+        gather = {'in_step': True, 'chunks': nck,
                   'alone_ms': float(gt[0]), 'bytes_per_rank': nbytes,
                   'link_bytes_per_peer': int(link),
                   'recv_gbs_per_rank':
-                  (world - 1) * args.gather_fanout * link
-                  / (float(gt[0]) * 1e-3) / 1e9,
-                  'how': args.gather, 'fanout': args.gather_fanout,
-                  'ctas': gather_ctas if coll is not None else None,
-                  'chunks_as_base_rows': base_chunks,
-                  'api': ('distributed.ChunkCollector: the rows of a chunk are '
-                          'produced in the rank\'s own result buffer and '
-                          'pushed into the result buffers of the other ranks '
-                          '(CUDA IPC peer memory over NVLink) by '
-                          + {'ce': 'the copy engines (snb_gather_rows_ce)',
-                             'bulk': 'one-warp CTAs driving the TMA unit '
-                             '(snb_gather_rows_bulk)',
-                             'stores': 'a kernel of 16-byte stores '
-                             '(snb_gather_rows)'}.get(args.gather, '') +
-                          ', a 4-byte all-reduce closes the step'
-                          + ('; %d chunks travel as base rows + '
-                             'normalisation table (a third of the bytes) and '
-                             'every receiver redoes the normalise + delta '
-                             'launch on them (bit-identical rows)'
-                             % base_chunks if base_chunks else '')
-                          if coll is not None else
-                          'all_gather_into_tensor of every chunk (NCCL over '
-                          'NVLink)') + '; on a second stream, chunk k travels '
-                         'while chunk k + 1 is computed; `alone_ms` is the '
-                         'same collection without compute'}
+                  (world - 1) * fan * link / (float(gt[0]) * 1e-3) / 1e9,
+                  'how': C['how'], 'fanout': fan, 'ctas': C['ctas'],
+                  'chunks_as_base_rows': len(as_base),
+                  'calibration_ms_per_step': calibration,
+                  'api': 'distributed.ChunkCollector: the rows of a chunk are '
+                         + what[C['how']] + ' on a second stream while the '
+                         'next chunk is computed'
+                         + ('; %d chunks travel as base rows + normalisation '
+                            'table (a third of the bytes) and every receiver '
+                            'redoes the normalise + delta launch on them '
+                            '(bit-identical rows)' % len(as_base)
+                            if as_base else '')
+                         + '; `alone_ms` is the same collection without the '
+                         'extraction; with --gather auto the method and the '
+                         'number of base-row chunks are the fastest of the '
+                         'trials in `calibration_ms_per_step` (run before '
+                         'the warm-up)'}
         # the gathered result of the last step against the local rows
         mine = torch.cat([g[rank] for g in gathered])
         gather['own_rows_intact'] = bool(torch.equal(mine, out))

@@ -377,6 +377,29 @@ int snb_read_segments(const char *const *paths, const int64_t *offsets,
                       const int64_t *nbytes, void *const *dst, int64_t n,
                       int32_t nthreads, int64_t *first_failed);
 
+/* ---- sample-rate conversion on the device -----------------------
+ * The reference resamples one utterance at a time on the host with sox or
+ * scipy (audio.py:358-423).  Here: Kaldi's LinearResample (resample.cc, the
+ * algorithm of kaldi::ResampleWaveform and of this path's pitch extractor) as
+ * a polyphase filter over a packed int16 batch already on the device.
+ * lowpass_cutoff <= 0: 0.99 * 0.5 * min(rate_in, rate_out); num_zeros <= 0: 6. */
+typedef struct snb_resampler snb_resampler;
+int snb_resampler_create(int32_t rate_in, int32_t rate_out, float lowpass_cutoff,
+                         int32_t num_zeros, snb_resampler **out);
+void snb_resampler_destroy(snb_resampler *r);
+/* samples an utterance of `nsamples` gives (the resampler is flushed) */
+int64_t snb_resampler_num_out(const snb_resampler *r, int64_t nsamples);
+/* utterance u: d_pcm[d_begin[u] .. + d_len[u]) -> d_out[d_out_begin[u] .. +
+ * snb_resampler_num_out(d_len[u])), as float32 (d_out_f32) and / or int16
+ * truncated toward zero and saturated (d_out_i16) -- either may be NULL.
+ * `max_out` bounds the outputs of one utterance, d_counts is an int64 scratch
+ * of nutts elements (receives the output counts).  nutts <= 65535. */
+int snb_resample_batch(const snb_resampler *r, const int16_t *d_pcm,
+                       const int64_t *d_begin, const int64_t *d_len,
+                       const int64_t *d_out_begin, int64_t nutts, int64_t max_out,
+                       float *d_out_f32, int16_t *d_out_i16, int64_t *d_counts,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

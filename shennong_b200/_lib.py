@@ -150,6 +150,10 @@ SIGNATURES = {
     'snb_gather_rows_bulk': (ctypes.c_int, [vp, i64, vp, i32, i64, i32, vp]),
     'snb_gather_rows_ce': (ctypes.c_int, [vp, i64, vp, i32, i64, vp]),
     'snb_wav_scan_batch': (ctypes.c_int, [vp, i64, vp, vp, vp, i32]),
+    'snb_resampler_create': (ctypes.c_int, [i32, i32, ctypes.c_float, i32, vp]),
+    'snb_resampler_destroy': (None, [vp]),
+    'snb_resampler_num_out': (i64, [vp, i64]),
+    'snb_resample_batch': (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp]),
     'snb_read_segments': (ctypes.c_int, [vp, vp, vp, vp, i64, i32, vp]),
 }
 

@@ -191,12 +191,17 @@ class Audio:
         Same call surface as the reference (shennong/audio.py:358-423):
         `backend` is 'sox' or 'scipy'.  The sox binary is not available to this
         engine, so both names run the FFT method of scipy.signal -- what the
-        reference itself falls back to without sox.
+        reference itself falls back to without sox.  One more backend exists
+        here: 'kaldi' converts mono int16 audio on the GPU with Kaldi's
+        LinearResample (``snb_resample_batch``; whole batches:
+        :func:`shennong_b200.engine.resample_packed`).
         """
-        if backend not in ('sox', 'scipy'):
+        if backend not in ('sox', 'scipy', 'kaldi'):
             raise ValueError(f'backend must be sox or scipy, it is {backend}')
         if sample_rate == self.sample_rate:
             return self
+        if backend == 'kaldi':
+            return self._resample_device(sample_rate)
         try:
             nsamples = int(self.nsamples * sample_rate / self.sample_rate)
             if sample_rate <= 0 or nsamples <= 0:
@@ -207,6 +212,24 @@ class Audio:
         except (ValueError, ZeroDivisionError):
             raise ValueError(f'resampling at {sample_rate} failed!') from None
         return Audio(data.astype(self.dtype), sample_rate, validate=False)
+
+    def _resample_device(self, sample_rate):
+        from shennong_b200 import engine
+        if self.nchannels != 1 or self.dtype != np.int16:
+            raise ValueError(
+                'the kaldi backend resamples mono int16 audio (use '
+                'astype(np.int16) and channel())')
+        try:
+            packed = engine.resample_packed(
+                engine.PackedAudio([self.data]), int(self.sample_rate),
+                int(sample_rate))
+        except (ValueError, RuntimeError) as err:
+            if 'CUDA device' in str(err):
+                raise
+            raise ValueError(f'resampling at {sample_rate} failed!') from None
+        n = int(packed.lengths[0])
+        return Audio(packed.dev[:n].cpu().numpy(), sample_rate,
+                     validate=False)
 
     @staticmethod
     def _is_valid_dtype(dtype):

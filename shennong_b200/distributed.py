@@ -256,6 +256,23 @@ def _ceil4(n):
     return (int(n) + 3) // 4 * 4
 
 
+class _LocalBuffer:
+    """the result buffer of a rank when the collection is an NCCL all-gather
+    (same interface as :class:`PeerGather`, nothing is mapped by the peers)"""
+    fanout = 1
+
+    def __init__(self, nfloats):
+        import torch
+        self.tensor = torch.empty(int(nfloats), dtype=torch.float32,
+                                  device='cuda')
+
+    def arrive(self):
+        pass
+
+    def close(self):
+        self.tensor = None
+
+
 class ChunkCollector:
     """Collection of a chunked, device-resident extraction inside the step
 
@@ -308,7 +325,16 @@ class ChunkCollector:
         self.stride = [_ceil4(r * D) for r in self.rows]
         self.at = np.concatenate(
             ([0], np.cumsum([self.size * st for st in self.stride])))
-        self.peers = PeerGather(int(self.at[-1]), group, fanout)
+        self.group = group
+        nccl = how == 'nccl'
+        self.peers = (_LocalBuffer(self.at[-1]) if nccl
+                      else PeerGather(int(self.at[-1]), group, fanout))
+        # NCCL gathers from a buffer of its own (no aliasing of input and
+        # output); the peer pushes read the rank's block of the result
+        self.own = None
+        if nccl:
+            self.own = [torch.empty(st, dtype=torch.float32, device='cuda')
+                        for st in self.stride]
         self.staging = None
         self.bstride, self.nstride, self.bat = {}, {}, {}
         self.layouts, self.nutts = {}, {}
@@ -323,7 +349,12 @@ class ChunkCollector:
                 at += self.size * (self.bstride[k] + self.nstride[k])
                 self.layouts[k] = engine.RowLayout(
                     frame_offsets=self.offsets[k])
-            self.staging = PeerGather(at, group, fanout)
+            self.staging = (_LocalBuffer(at) if nccl
+                            else PeerGather(at, group, fanout))
+            if nccl:
+                self.own_base = {k: torch.empty(
+                    self.bstride[k] + self.nstride[k], dtype=torch.float32,
+                    device='cuda') for k in self.base_ids}
         self.comm = torch.cuda.Stream()
         self._base_arrived = None
 
@@ -335,6 +366,9 @@ class ChunkCollector:
 
     def out_view(self, k):
         """[rows_k, D]: where this rank's pipeline writes chunk k"""
+        if self.own is not None:
+            return self.own[k][:self.rows[k] * self.pipe.out_dim].view(
+                self.rows[k], self.pipe.out_dim)
         return self._block(k, self.rank)
 
     def result(self, k):
@@ -358,11 +392,23 @@ class ChunkCollector:
     def base_view(self, k):
         """[rows_k, d] buffer for the base rows of chunk k (``base_buf`` of
         ``run_device``) when the chunk travels as base rows, else None"""
-        return self._base_block(k, self.rank) if k in self.bat else None
+        if k not in self.bat:
+            return None
+        if self.own is not None:
+            d = self.pipe.base_dim
+            return self.own_base[k][:self.rows[k] * d].view(self.rows[k], d)
+        return self._base_block(k, self.rank)
 
     def norm_view(self, k):
         """``norm_out`` of ``run_device`` for chunk k (or None)"""
-        return self._norm_block(k, self.rank) if k in self.bat else None
+        if k not in self.bat or not self.nstride[k]:
+            return None
+        if self.own is not None:
+            d = self.pipe.base_dim
+            a = self.bstride[k]
+            return self.own_base[k][a:a + self.nutts[k] * 2 * d].view(
+                self.nutts[k], 2, d)
+        return self._norm_block(k, self.rank)
 
     # -- the step --------------------------------------------------------------
     def collect(self, k):
@@ -376,7 +422,9 @@ class ChunkCollector:
         done.record(cur)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(done)
-            if k in self.bat:
+            if self.own is not None:
+                self._collect_nccl(k)
+            elif k in self.bat:
                 a = self.bat[k] + self.rank * self.bstride[k]
                 src = self.staging.tensor[a:a + self.bstride[k]]
                 self.staging.push(src, a, ctas=self.ctas, how=self.how)
@@ -387,12 +435,35 @@ class ChunkCollector:
                     self.staging.push(src, a, ctas=self.ctas, how=self.how)
                 if k == self.base_ids[-1]:
                     self.staging.arrive()
-                    self._base_arrived = torch.cuda.Event()
-                    self._base_arrived.record(self.comm)
             else:
                 a = int(self.at[k]) + self.rank * self.stride[k]
                 src = self.peers.tensor[a:a + self.stride[k]]
                 self.peers.push(src, a, ctas=self.ctas, how=self.how)
+            if self.base_ids and k == self.base_ids[-1]:
+                self._base_arrived = torch.cuda.Event()
+                self._base_arrived.record(self.comm)
+
+    def _collect_nccl(self, k):
+        """all-gathers of chunk k (the collective completes with the data of
+        every rank in place: no separate arrival)"""
+        dist = _dist()
+        if k in self.bat:
+            a, n = self.bat[k], self.bstride[k]
+            dist.all_gather_into_tensor(
+                self.staging.tensor[a:a + self.size * n],
+                self.own_base[k][:n], group=self.group)
+            if self.nstride[k]:
+                a, m = a + self.size * n, self.nstride[k]
+                dist.all_gather_into_tensor(
+                    self.staging.tensor[a:a + self.size * m],
+                    self.own_base[k][n:n + m], group=self.group)
+            # this rank's final rows of the chunk stay local
+            self._block(k, self.rank).copy_(self.out_view(k))
+        else:
+            a, n = int(self.at[k]), self.stride[k]
+            dist.all_gather_into_tensor(
+                self.peers.tensor[a:a + self.size * n], self.own[k],
+                group=self.group)
 
     def finish(self):
         """Queues the end of the step on the current stream: the receivers'

@@ -410,6 +410,82 @@ def process_pitch(post_opts, raw, layout, seed=0, out=None, out_layout=None):
 # --------------------------------------------------------------------------
 # helpers for the host API
 # --------------------------------------------------------------------------
+class Resampler:
+    """snb_resampler handle: Kaldi's LinearResample between two sample rates
+    (cached per (rate_in, rate_out, cutoff, zeros) and device)"""
+    _cache = {}
+    _lock = threading.Lock()
+
+    def __init__(self, rate_in, rate_out, lowpass_cutoff=0.0, num_zeros=0):
+        require_cuda()
+        self.rate_in, self.rate_out = int(rate_in), int(rate_out)
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().snb_resampler_create(
+            self.rate_in, self.rate_out, float(lowpass_cutoff),
+            int(num_zeros), ctypes.byref(handle)))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _lib.lib().snb_resampler_destroy(self.handle)
+        except Exception:
+            pass
+
+    @classmethod
+    def get(cls, rate_in, rate_out, lowpass_cutoff=0.0, num_zeros=0):
+        torch = require_cuda()
+        key = (int(rate_in), int(rate_out), float(lowpass_cutoff),
+               int(num_zeros), torch.cuda.current_device())
+        with cls._lock:
+            if key not in cls._cache:
+                cls._cache[key] = cls(rate_in, rate_out, lowpass_cutoff,
+                                      num_zeros)
+            return cls._cache[key]
+
+    def num_out(self, nsamples):
+        return int(_lib.lib().snb_resampler_num_out(self.handle, int(nsamples)))
+
+
+def resample_packed(packed, rate_in, rate_out, lowpass_cutoff=0.0,
+                    num_zeros=0, float32=False):
+    """Sample-rate conversion of every utterance of an int16
+    :class:`PackedAudio` on the device (``snb_resample_batch``)
+
+    Returns a new PackedAudio at `rate_out` whose device buffer holds the
+    int16 result (truncated toward zero like the reference's
+    ``.astype(np.int16)``, audio.py:423), every utterance on a 16-byte
+    boundary -- ready for the feature kernels, nothing goes through the host
+    -- and, with `float32`, also the float32 device tensor of the same
+    geometry (bit-equal to the CPU oracle).
+    """
+    torch = require_cuda()
+    if packed.is_float:
+        raise ValueError('int16 audio expected')
+    rs = Resampler.get(rate_in, rate_out, lowpass_cutoff, num_zeros)
+    lengths = np.array([rs.num_out(n) for n in packed.lengths], dtype=np.int64)
+    padded = (lengths + _ALIGN - 1) // _ALIGN * _ALIGN
+    starts = np.concatenate(([0], np.cumsum(padded)))[:-1].astype(np.int64)
+    total = int(padded.sum()) + _PAD
+    out = torch.zeros(total, dtype=torch.int16, device='cuda')
+    outf = (torch.zeros(total, dtype=torch.float32, device='cuda')
+            if float32 else None)
+    nutts = packed.nutts
+    step = 65535
+    for b in range(0, nutts, step):
+        e = min(b + step, nutts)
+        desc = torch.from_numpy(np.concatenate(
+            [packed.starts[b:e], packed.lengths[b:e], starts[b:e]])).to('cuda')
+        counts = torch.empty(e - b, dtype=torch.int64, device='cuda')
+        n = e - b
+        _lib.check(_lib.lib().snb_resample_batch(
+            rs.handle, _ptr(packed.dev), _ptr(desc[:n]), _ptr(desc[n:2 * n]),
+            _ptr(desc[2 * n:]), n, int(lengths[b:e].max()) if n else 0,
+            _ptr(outf), _ptr(out), _ptr(counts), _stream_ptr()))
+    result = PackedAudio.from_packed(None, starts, lengths, dev=out)
+    return (result, outf) if float32 else result
+
+
 def num_frames_array(frame_opts, lengths):
     """Vectorised snb_num_frames (NumFrames with flush, frames.py:137) for an
     int64 array of utterance lengths"""

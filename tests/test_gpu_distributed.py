@@ -89,7 +89,8 @@ WORKER = textwrap.dedent('''
     want_local, _, _, _ = pipe.run_device(engine.PackedAudio(mine))
     want = [torch.empty_like(want_local) for _ in range(size)]
     dist.all_gather(want, want_local.contiguous())
-    for how, nb in (('ce', 0), ('ce', 2), ('bulk', 3), ('stores', 1)):
+    for how, nb in (('ce', 0), ('ce', 2), ('bulk', 3), ('stores', 1),
+                    ('nccl', 0), ('nccl', 2)):
         coll = ChunkCollector(
             pipe, [b['feat'].frame_offsets for b in batches], how=how,
             base_chunks=nb, ctas=8)
