@@ -616,11 +616,17 @@ def main():
             calibration['%s/%d' % (how, nb0)] = trial_ms()
         best = min(calibration, key=calibration.get).split('/')[0]
         if hybrid_ok and args.gather_base_chunks < 0 and links >= 3:
-            # and the number of base-row chunks around the default
-            for nb in sorted({max(nb0 - 1, 0), min(nb0 + 1, len(chunks) - 1),
-                              min(nb0 + 2, len(chunks) - 1)} - {nb0}):
-                set_collection(best, nb)
-                calibration['%s/%d' % (best, nb)] = trial_ms()
+            # and the number of base-row chunks: walk away from the default
+            # while the step gets faster
+            for direction in (1, -1):
+                nb, last = nb0, calibration['%s/%d' % (best, nb0)]
+                while 0 <= nb + direction <= len(chunks) - 1:
+                    nb += direction
+                    set_collection(best, nb)
+                    t = calibration['%s/%d' % (best, nb)] = trial_ms()
+                    if t >= last:
+                        break
+                    last = t
         how, nb = min(calibration, key=calibration.get).split('/')
         if (how, int(nb)) != (C['how'], C['base_chunks']):
             set_collection(how, int(nb))
