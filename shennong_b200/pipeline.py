@@ -608,7 +608,8 @@ def _assemble(manager, proc, delta, pitch, cmvn_mode, utts, audios, warps,
             cmvn = manager.get_cmvn_processor()
             group = names.index(utt.speaker) if names is not None else i
             cmvn.add_stats(stats[group])
-            if block.shape[0] and cmvn.count < 1.0:
+            if cmvn.count < 1.0:      # (whatever the utterance's length:
+                # the reference raises in cmvn.process, cmvn.py:204-214)
                 raise ValueError(
                     'insufficient accumulation of stats for CMVN, '
                     'must be >= 1.0 but is {}'.format(cmvn.count))
