@@ -387,3 +387,20 @@ except ModuleNotFoundError:
                          text=True, cwd=root, timeout=300)
     assert res.returncode == 0 and res.stdout.strip() == 'ok', (
         res.stdout + res.stderr)
+
+
+def test_bench_corpus_generator_is_the_tests_generator():
+    """both arms of bench.py (and the parity check inside it) read utterances
+    of the same seeded generator the tests use"""
+    import importlib.util
+    import os
+    from conftest import ROOT, synth_utterance
+    spec = importlib.util.spec_from_file_location(
+        'snb_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for index in (0, 7, 2047):
+        assert np.array_equal(bench.synth_utterance(index, 16000),
+                              synth_utterance(index, 16000))
+    block = bench.synth_host(3, 2)
+    assert np.array_equal(block[:bench.UTT_SAMPLES], bench.synth_utterance(3))
